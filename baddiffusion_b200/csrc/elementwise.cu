@@ -1,0 +1,564 @@
+// HBM-bound fused kernels of the BadDiffusion hot path: batch-prep (K11), MSE (K12), scheduler steps (K13),
+// image finalisation (K14), up/down-sampling helpers, weight packing and the optimizer tail.
+// Arithmetic that the reference performs as separate fp32 torch ops uses *_rn intrinsics (no FMA
+// contraction) in the reference's association order so results are bit-identical.
+#include "common.cuh"
+
+#include <stdarg.h>
+
+namespace bd {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* get_error() { return g_err; }
+
+static unsigned long long g_launches = 0;
+void count_launch(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+unsigned long long launches() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+int num_sms() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  if (cached[dev] == 0) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    cached[dev] = n > 0 ? n : 148;
+  }
+  return cached[dev];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 + Box-Muller (perf-mode noise; parity mode passes the reference's CPU-drawn noise)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
+__device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset, uint64_t idx4) {
+  uint4 c = make_uint4((uint32_t)idx4, (uint32_t)(idx4 >> 32), (uint32_t)offset, (uint32_t)(offset >> 32));
+  uint4 r = philox4x32_10(c, make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+  const float k = 2.3283064365386963e-10f;  // 2^-32
+  float u0 = (r.x + 0.5f) * k, u1 = (r.y + 0.5f) * k, u2 = (r.z + 0.5f) * k, u3 = (r.w + 0.5f) * k;
+  float r0 = sqrtf(-2.0f * __logf(u0)), r1 = sqrtf(-2.0f * __logf(u2));
+  float s0, c0, s1, c1;
+  __sincosf(6.283185307179586f * u1, &s0, &c0);
+  __sincosf(6.283185307179586f * u3, &s1, &c1);
+  return make_float4(r0 * c0, r0 * s0, r1 * c1, r1 * s1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K11 batch-prep.  One thread = 4 consecutive elements of one sample (float4 I/O, HW % 4 == 0).
+// Algorithmic bytes / element: img 4 (+ noise 4) + x_noisy 4 + target 4 = 12..16 B.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) batch_prep_kernel(
+    const float* __restrict__ img, const uint8_t* __restrict__ is_poison, const float* __restrict__ trigger,
+    const float* __restrict__ target, const float* __restrict__ R_explicit, const float* __restrict__ noise,
+    const int64_t* __restrict__ t, const float* __restrict__ alphas, const float* __restrict__ acp,
+    float* __restrict__ x_noisy, float* __restrict__ eps_target, float* __restrict__ noise_out, int B, int CHW4,
+    uint64_t seed, uint64_t offset) {
+  const int b = blockIdx.y;
+  const int64_t ti = t[b];
+  const float al = alphas[ti], ac = acp[ti];
+  // loss.py:268-270 and scheduling_ddpm.py:432-438, same op order, each op rounded separately
+  const float a = __fsqrt_rn(ac);
+  const float s = __fsqrt_rn(__fsub_rn(1.0f, ac));
+  const float rho = __fdiv_rn(__fmul_rn(__fsub_rn(1.0f, __fsqrt_rn(al)), s), __fsub_rn(1.0f, al));
+  const float one_m_a = __fsub_rn(1.0f, a);
+  const bool poison = is_poison ? (is_poison[b] != 0) : false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHW4; i += gridDim.x * blockDim.x) {
+    const size_t g = (size_t)b * CHW4 + i;
+    float4 im = reinterpret_cast<const float4*>(img)[g];
+    float4 e;
+    if (noise) e = reinterpret_cast<const float4*>(noise)[g];
+    else e = philox_normal4(seed, offset, g);
+    float x0[4] = {im.x, im.y, im.z, im.w}, R[4] = {0.f, 0.f, 0.f, 0.f}, ev[4] = {e.x, e.y, e.z, e.w};
+    if (R_explicit) {
+      float4 r = reinterpret_cast<const float4*>(R_explicit)[g];
+      R[0] = r.x; R[1] = r.y; R[2] = r.z; R[3] = r.w;
+    } else if (poison) {
+      float4 gt = reinterpret_cast<const float4*>(trigger)[i];
+      float4 yt = reinterpret_cast<const float4*>(target)[i];
+      float gv[4] = {gt.x, gt.y, gt.z, gt.w}, yv[4] = {yt.x, yt.y, yt.z, yt.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        R[k] = (gv[k] > -1.0f) ? gv[k] : x0[k];  // dataset.py:276,312-313: M*img + (1-M)*g, M in {0,1}
+        x0[k] = yv[k];                           // dataset.py:314
+      }
+    }
+    float xn[4], tg[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float noisy = __fadd_rn(__fmul_rn(a, x0[k]), __fmul_rn(s, ev[k]));  // add_noise
+      xn[k] = __fadd_rn(noisy, __fmul_rn(one_m_a, R[k]));                 // loss.py:285 (first)
+      tg[k] = __fadd_rn(__fmul_rn(rho, R[k]), ev[k]);                     // loss.py:285 (second)
+    }
+    reinterpret_cast<float4*>(x_noisy)[g] = make_float4(xn[0], xn[1], xn[2], xn[3]);
+    reinterpret_cast<float4*>(eps_target)[g] = make_float4(tg[0], tg[1], tg[2], tg[3]);
+    if (noise_out) reinterpret_cast<float4*>(noise_out)[g] = e;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K12 MSE forward + gradient; deterministic two-stage reduction.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMsePartials = 1024;
+__global__ void __launch_bounds__(256) mse_partial_kernel(const float* __restrict__ eps_hat,
+                                                          const float* __restrict__ target, float* __restrict__ grad,
+                                                          float* __restrict__ partial,
+                                                          const float* __restrict__ loss_scale, size_t n) {
+  const float gs = (loss_scale ? *loss_scale : 1.0f) * 2.0f / (float)n;
+  double acc = 0.0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float d = eps_hat[i] - target[i];
+    acc += (double)d * (double)d;
+    if (grad) grad[i] = d * gs;
+  }
+  acc = warp_sum_d(acc);
+  __shared__ double sm[8];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int i = 0; i < 8; ++i) s += sm[i];
+    partial[blockIdx.x] = (float)s;
+  }
+}
+__global__ void mse_final_kernel(const float* __restrict__ partial, int np, float* __restrict__ loss, size_t n) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < np; i += 32) acc += (double)partial[i];
+  acc = warp_sum_d(acc);
+  if (threadIdx.x == 0) *loss = (float)(acc / (double)n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K13 scheduler steps
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ddpm_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                        const float* __restrict__ z, float* __restrict__ out,
+                                                        const float* __restrict__ coef,
+                                                        const int* __restrict__ step_index, size_t n4, uint64_t seed,
+                                                        uint64_t offset) {
+  const int row = step_index ? *step_index : 0;
+  const float* c = coef + (size_t)row * 8;
+  const float sb = c[0], sa = c[1], c0 = c[2], ct = c[3], sigma = c[4], clip = c[5], clipd = c[6];
+  const bool has_noise = c[7] != 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 xv = reinterpret_cast<const float4*>(x)[i], ev = reinterpret_cast<const float4*>(eps)[i];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + (uint64_t)row, i);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      // scheduling_ddpm.py:372 pred_original_sample = (sample - beta_prod_t**0.5 * model_output) / alpha_prod_t**0.5
+      float x0 = __fdiv_rn(__fsub_rn(xs[k], __fmul_rn(sb, es[k])), sa);
+      if (clip > 0.0f) x0 = fminf(fmaxf(x0, -clip), clip);  // :387-390
+      // :399 pred_prev_sample = c0 * x0 + ct * sample
+      float mu = __fadd_rn(__fmul_rn(c0, x0), __fmul_rn(ct, xs[k]));
+      // :411,413 + variance**0.5 * noise  (t > 0)
+      float r = has_noise ? __fadd_rn(mu, __fmul_rn(sigma, zs[k])) : mu;
+      if (clipd > 0.0f) r = fminf(fmaxf(r, -clipd), clipd);  // :414-415 (BadDiffusion patch)
+      o[k] = r;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                        const float* __restrict__ z, float* __restrict__ out,
+                                                        const float* __restrict__ coef,
+                                                        const int* __restrict__ step_index, size_t n4, uint64_t seed,
+                                                        uint64_t offset) {
+  const int row = step_index ? *step_index : 0;
+  const float* c = coef + (size_t)row * 8;
+  const float sb = c[0], sa = c[1], sap = c[2], dirc = c[3], stdv = c[4], clip = c[5];
+  const bool reclip = c[6] != 0.0f, has_noise = stdv > 0.0f;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 xv = reinterpret_cast<const float4*>(x)[i], ev = reinterpret_cast<const float4*>(eps)[i];
+    float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + (uint64_t)row, i);
+    float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float x0 = __fdiv_rn(__fsub_rn(xs[k], __fmul_rn(sb, es[k])), sa);  // scheduling_ddim.py:333
+      float pe = es[k];
+      if (clip > 0.0f) x0 = fminf(fmaxf(x0, -clip), clip);               // :347-352
+      if (reclip) pe = __fdiv_rn(__fsub_rn(xs[k], __fmul_rn(sa, x0)), sb);  // :361
+      float dir = __fmul_rn(dirc, pe);                                   // :364
+      float r = __fadd_rn(__fmul_rn(sap, x0), dir);                      // :367
+      if (has_noise) r = __fadd_rn(r, __fmul_rn(stdv, zs[k]));           // :380-382
+      o[k] = r;
+    }
+    reinterpret_cast<float4*>(out)[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void sampler_advance_kernel(int* step_index, const int64_t* __restrict__ timesteps, int64_t* t_vec, int B,
+                                       int first) {
+  int idx = first ? 0 : (*step_index + 1);
+  __syncthreads();
+  for (int i = threadIdx.x; i < B; i += blockDim.x) t_vec[i] = timesteps[idx];
+  if (threadIdx.x == 0) *step_index = idx;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K14 finalize: NCHW f32 -> NHWC clamp(x/2+0.5,0,1) (f32) and/or u8
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ x, float* __restrict__ o01,
+                                                       uint8_t* __restrict__ ou8, int B, int C, int HW) {
+  size_t n = (size_t)B * C * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // i indexes the NHWC output: ((b*HW + p)*C + c)
+    int c = (int)(i % C);
+    size_t bp = i / C;
+    int p = (int)(bp % HW);
+    size_t b = bp / HW;
+    float v = x[(b * C + c) * HW + p];
+    v = __fadd_rn(__fdiv_rn(v, 2.0f), 0.5f);  // pipeline_ddpm.py:115
+    v = fminf(fmaxf(v, 0.0f), 1.0f);
+    if (o01) o01[i] = v;
+    if (ou8) ou8[i] = (uint8_t)rintf(__fmul_rn(v, 255.0f));  // model.py:499 (numpy round = half-to-even)
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nearest 2x upsample and its adjoint; f16 add; 8 channels (16 B) per thread
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) upsample2x_kernel(const __half* __restrict__ x, int64_t ldx,
+                                                         __half* __restrict__ y, int64_t ldy, int B, int H, int W,
+                                                         int C8) {
+  size_t n = (size_t)B * 2 * H * 2 * W * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    size_t p = i / C8;
+    int wo = (int)(p % (2 * W));
+    size_t q = p / (2 * W);
+    int ho = (int)(q % (2 * H));
+    size_t b = q / (2 * H);
+    size_t src = (b * H + (ho >> 1)) * W + (wo >> 1);
+    *reinterpret_cast<half8*>(y + p * ldy + c * 8) = *reinterpret_cast<const half8*>(x + src * ldx + c * 8);
+  }
+}
+__global__ void __launch_bounds__(256) upsample2x_bwd_kernel(const __half* __restrict__ dy, int64_t ldy,
+                                                             __half* __restrict__ dx, int64_t ldx, int B, int H, int W,
+                                                             int C8) {
+  size_t n = (size_t)B * H * W * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    size_t p = i / C8;
+    int w = (int)(p % W);
+    size_t q = p / W;
+    int h = (int)(q % H);
+    size_t b = q / H;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, f[8];
+#pragma unroll
+    for (int dh = 0; dh < 2; ++dh)
+#pragma unroll
+      for (int dw = 0; dw < 2; ++dw) {
+        size_t src = (b * 2 * H + 2 * h + dh) * (2 * W) + 2 * w + dw;
+        unpack8(*reinterpret_cast<const half8*>(dy + src * ldy + c * 8), f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] += f[k];
+      }
+    *reinterpret_cast<half8*>(dx + p * ldx + c * 8) = pack8(acc);
+  }
+}
+__global__ void __launch_bounds__(256) add_f16_kernel(const __half* __restrict__ a, int64_t lda,
+                                                      const __half* __restrict__ b, int64_t ldb,
+                                                      __half* __restrict__ y, int64_t ldy, int64_t rows, int C8) {
+  size_t n = (size_t)rows * C8;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    int c = (int)(i % C8);
+    size_t r = i / C8;
+    float fa[8], fb[8];
+    unpack8(*reinterpret_cast<const half8*>(a + r * lda + c * 8), fa);
+    if (b) {
+      unpack8(*reinterpret_cast<const half8*>(b + r * ldb + c * 8), fb);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+    }
+    *reinterpret_cast<half8*>(y + r * ldy + c * 8) = pack8(fa);
+  }
+}
+
+// OIHW f32 -> f16 [tap][O][I] and [tap][I][O]
+__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ wf,
+                                                          __half* __restrict__ wd, int O, int I, int taps) {
+  size_t n = (size_t)O * I * taps;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    // i indexes the source (o, ci, tap)
+    int tap = (int)(i % taps);
+    size_t r = i / taps;
+    int ci = (int)(r % I);
+    int o = (int)(r / I);
+    __half h = __float2half_rn(w[i]);
+    if (wf) wf[((size_t)tap * O + o) * I + ci] = h;
+    if (wd) wd[((size_t)tap * I + ci) * O + o] = h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// optimizer tail.  state = {loss_scale, growth_tracker, found_inf, grad_norm(unscaled), skipped}
+// ---------------------------------------------------------------------------------------------
+constexpr int kNormPartials = 1024;
+__global__ void __launch_bounds__(256) gradnorm_partial_kernel(const float* __restrict__ g, size_t n,
+                                                               float* __restrict__ partial) {
+  double acc = 0.0;
+  int bad = 0;
+  size_t n4 = n / 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(g)[i];
+    float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    if (!isfinite(s)) bad = 1;
+    acc += (double)s;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+    float v = g[n4 * 4 + threadIdx.x];
+    if (!isfinite(v)) bad = 1;
+    acc += (double)v * v;
+  }
+  acc = warp_sum_d(acc);
+  bad = __any_sync(0xffffffffu, bad);
+  __shared__ double sm[8];
+  __shared__ int sb[8];
+  if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = acc; sb[threadIdx.x >> 5] = bad; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    int b = 0;
+    for (int i = 0; i < 8; ++i) { s += sm[i]; b |= sb[i]; }
+    partial[blockIdx.x] = b ? INFINITY : (float)s;
+  }
+}
+__global__ void gradnorm_final_kernel(const float* __restrict__ partial, int np, float* __restrict__ state) {
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < np; i += 32) acc += (double)partial[i];
+  acc = warp_sum_d(acc);
+  if (threadIdx.x == 0) {
+    float scale = state[0];
+    bool bad = !isfinite((float)acc) || !isfinite(acc);
+    state[2] = bad ? 1.0f : 0.0f;
+    state[3] = bad ? INFINITY : (float)(sqrt(acc) / (double)scale);
+  }
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                   float* __restrict__ m, float* __restrict__ v, size_t n,
+                                                   const float* __restrict__ lr_p, float b1, float b2, float eps,
+                                                   float wd, float max_norm, const int* __restrict__ step_p,
+                                                   const float* __restrict__ state) {
+  if (state[2] != 0.0f) return;  // found_inf: skip the step (GradScaler semantics)
+  const float lr = *lr_p;
+  const int step = *step_p + 1;
+  // unscale and clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))
+  float coef = 1.0f / state[0];
+  if (max_norm > 0.0f) coef *= fminf(1.0f, max_norm / (state[3] + 1e-6f));
+  const float bc1 = 1.0f - powf(b1, (float)step), bc2 = 1.0f - powf(b2, (float)step);
+  const float step_size = lr / bc1, bc2_sqrt = sqrtf(bc2);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    float gi = g[i] * coef, pi = p[i];
+    if (wd != 0.0f) gi += wd * pi;
+    float mi = m[i] + (1.0f - b1) * (gi - m[i]);  // lerp, torch/optim/adam.py single-tensor path
+    float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+    float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] = pi - step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+  }
+}
+__global__ void scaler_update_kernel(float* state, int* step, float growth, float backoff, int interval) {
+  if (state[2] != 0.0f) {
+    state[0] *= backoff;
+    state[1] = 0.0f;
+    state[4] += 1.0f;
+  } else {
+    *step += 1;
+    state[1] += 1.0f;
+    if ((int)state[1] >= interval) {
+      state[0] *= growth;
+      state[1] = 0.0f;
+    }
+  }
+}
+
+}  // namespace bd
+
+using namespace bd;
+
+static inline int grid_for(size_t n, int threads, int per_sm = 8) {
+  size_t want = (n + threads - 1) / threads;
+  size_t cap = (size_t)num_sms() * per_sm;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+extern "C" {
+
+int bd_version(void) { return 100; }
+const char* bd_last_error(void) { return bd::get_error(); }
+uint64_t bd_launch_count(void) { return bd::launches(); }
+int bd_device_supported(void) {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  return major == 10;
+}
+
+int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigger, const float* target,
+                  const float* R_explicit, const float* noise, const int64_t* t, const float* alphas,
+                  const float* alphas_cumprod, float* x_noisy, float* eps_target, float* noise_out, int B, int C,
+                  int H, int W, int T, uint64_t seed, uint64_t offset, void* stream) {
+  BD_CHECK_ARG(img && t && alphas && alphas_cumprod && x_noisy && eps_target, "bd_batch_prep: null pointer");
+  BD_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && T > 0, "bd_batch_prep: bad shape");
+  BD_CHECK_ARG(((size_t)C * H * W) % 4 == 0, "bd_batch_prep: C*H*W must be a multiple of 4");
+  BD_CHECK_ARG(!is_poison || R_explicit || (trigger && target), "bd_batch_prep: trigger/target required");
+  if (B == 0) return BD_OK;  // loss.py:288-289 (empty batch)
+  int chw4 = (int)((size_t)C * H * W / 4);
+  dim3 grid(ceil_div(chw4, 256) < 64 ? ceil_div(chw4, 256) : 64, B);
+  batch_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, is_poison, trigger, target, R_explicit, noise, t,
+                                                           alphas, alphas_cumprod, x_noisy, eps_target, noise_out, B,
+                                                           chw4, seed, offset);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+size_t bd_mse_workspace_floats(void) { return kMsePartials; }
+int bd_mse_fwd_bwd(const float* eps_hat, const float* target, float* loss, float* grad, float* partial,
+                   const float* loss_scale, size_t n, void* stream) {
+  BD_CHECK_ARG(eps_hat && target && loss && partial, "bd_mse_fwd_bwd: null pointer");
+  BD_CHECK_ARG(n > 0, "bd_mse_fwd_bwd: empty input");
+  int g = grid_for(n, 256, 4);
+  if (g > kMsePartials) g = kMsePartials;
+  mse_partial_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(eps_hat, target, grad, partial, loss_scale, n);
+  mse_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial, g, loss, n);
+  count_launch(2);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_ddpm_step(const float* x, const float* eps_hat, const float* z, float* x_prev, const float* coef,
+                 const int* step_index, size_t n, uint64_t seed, uint64_t offset, void* stream) {
+  BD_CHECK_ARG(x && eps_hat && x_prev && coef, "bd_ddpm_step: null pointer");
+  BD_CHECK_ARG(n % 4 == 0, "bd_ddpm_step: n must be a multiple of 4");
+  if (n == 0) return BD_OK;
+  ddpm_step_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, eps_hat, z, x_prev, coef, step_index,
+                                                                          n / 4, seed, offset);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_ddim_step(const float* x, const float* eps_hat, const float* z, float* x_prev, const float* coef,
+                 const int* step_index, size_t n, uint64_t seed, uint64_t offset, void* stream) {
+  BD_CHECK_ARG(x && eps_hat && x_prev && coef, "bd_ddim_step: null pointer");
+  BD_CHECK_ARG(n % 4 == 0, "bd_ddim_step: n must be a multiple of 4");
+  if (n == 0) return BD_OK;
+  ddim_step_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, eps_hat, z, x_prev, coef, step_index,
+                                                                          n / 4, seed, offset);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_sampler_advance(int* step_index, const int64_t* timesteps, int64_t* t_vec, int B, int first, void* stream) {
+  BD_CHECK_ARG(step_index && timesteps && t_vec && B > 0, "bd_sampler_advance: bad argument");
+  sampler_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(step_index, timesteps, t_vec, B, first);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_finalize_images(const float* x, float* nhwc01, uint8_t* nhwc_u8, int B, int C, int H, int W, void* stream) {
+  BD_CHECK_ARG(x && (nhwc01 || nhwc_u8), "bd_finalize_images: null pointer");
+  if (B == 0) return BD_OK;
+  size_t n = (size_t)B * C * H * W;
+  finalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, nhwc01, nhwc_u8, B, C, H * W);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_upsample2x(const void* x, int64_t ld_x, void* y, int64_t ld_y, int B, int H, int W, int C, void* stream) {
+  BD_CHECK_ARG(x && y && C % 8 == 0 && ld_x % 8 == 0 && ld_y % 8 == 0, "bd_upsample2x: C, ld must be multiples of 8");
+  size_t n = (size_t)B * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)x, ld_x, (__half*)y, ld_y, B, H,
+                                                                       W, C / 8);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_upsample2x_bwd(const void* dy, int64_t ld_dy, void* dx, int64_t ld_dx, int B, int H, int W, int C,
+                      void* stream) {
+  BD_CHECK_ARG(dy && dx && C % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0, "bd_upsample2x_bwd: bad argument");
+  size_t n = (size_t)B * H * W * (C / 8);
+  upsample2x_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)dy, ld_dy, (__half*)dx,
+                                                                           ld_dx, B, H, W, C / 8);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_add_f16(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* y, int64_t ld_y, int64_t rows, int C,
+               void* stream) {
+  BD_CHECK_ARG(a && y && C % 8 == 0 && ld_a % 8 == 0 && ld_y % 8 == 0 && (!b || ld_b % 8 == 0), "bd_add_f16: bad argument");
+  size_t n = (size_t)rows * (C / 8);
+  if (n == 0) return BD_OK;
+  add_f16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, ld_a, (const __half*)b, ld_b,
+                                                                    (__half*)y, ld_y, rows, C / 8);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int O, int I, int ksize, void* stream) {
+  BD_CHECK_ARG(w_oihw && (w_fwd || w_dgrad) && O > 0 && I > 0 && (ksize == 1 || ksize == 3), "bd_pack_conv_weight: bad argument");
+  size_t n = (size_t)O * I * ksize * ksize;
+  pack_weight_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (__half*)w_fwd, (__half*)w_dgrad, O, I,
+                                                                        ksize * ksize);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+size_t bd_gradnorm_workspace_floats(void) { return kNormPartials; }
+int bd_grad_norm(const float* grad, size_t n, float* partial, float* state, void* stream) {
+  BD_CHECK_ARG(grad && partial && state && n > 0, "bd_grad_norm: bad argument");
+  BD_CHECK_ARG(((uintptr_t)grad & 15) == 0, "bd_grad_norm: grad must be 16-byte aligned");
+  int g = grid_for(n / 4 + 1, 256, 4);
+  if (g > kNormPartials) g = kNormPartials;
+  gradnorm_partial_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(grad, n, partial);
+  gradnorm_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(partial, g, state);
+  count_launch(2);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* lr,
+                 float beta1, float beta2, float eps, float weight_decay, float max_norm, const int* step,
+                 float* state, void* stream) {
+  BD_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && lr && step && state && n > 0, "bd_adam_step: bad argument");
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
+                                                                 eps, weight_decay, max_norm, step, state);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_scaler_update(float* state, int* step, float growth, float backoff, int growth_interval, void* stream) {
+  BD_CHECK_ARG(state && step, "bd_scaler_update: null pointer");
+  scaler_update_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state, step, growth, backoff, growth_interval);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+}  // extern "C"
