@@ -12,6 +12,9 @@ namespace bd {
 
 // thread-local last-error string behind bd_last_error()
 void set_error(const char* fmt, ...);
+const char* get_error();
+void count_launch(int n);
+unsigned long long launches();
 
 #define BD_CHECK_ARG(cond, ...)                 \
   do {                                          \
@@ -31,7 +34,7 @@ void set_error(const char* fmt, ...);
     }                                                                            \
   } while (0)
 
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 

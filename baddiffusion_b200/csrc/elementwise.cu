@@ -295,22 +295,6 @@ __global__ void __launch_bounds__(256) add_f16_kernel(const __half* __restrict__
   }
 }
 
-// OIHW f32 -> f16 [tap][O][I] and [tap][I][O]
-__global__ void __launch_bounds__(256) pack_weight_kernel(const float* __restrict__ w, __half* __restrict__ wf,
-                                                          __half* __restrict__ wd, int O, int I, int taps) {
-  size_t n = (size_t)O * I * taps;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    // i indexes the source (o, ci, tap)
-    int tap = (int)(i % taps);
-    size_t r = i / taps;
-    int ci = (int)(r % I);
-    int o = (int)(r / I);
-    __half h = __float2half_rn(w[i]);
-    if (wf) wf[((size_t)tap * O + o) * I + ci] = h;
-    if (wd) wd[((size_t)tap * I + ci) * O + o] = h;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // optimizer tail.  state = {loss_scale, growth_tracker, found_inf, grad_norm(unscaled), skipped}
 // ---------------------------------------------------------------------------------------------
@@ -516,16 +500,6 @@ int bd_add_f16(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* y
   if (n == 0) return BD_OK;
   add_f16_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, ld_a, (const __half*)b, ld_b,
                                                                     (__half*)y, ld_y, rows, C / 8);
-  count_launch(1);
-  BD_CHECK_LAUNCH();
-  return BD_OK;
-}
-
-int bd_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int O, int I, int ksize, void* stream) {
-  BD_CHECK_ARG(w_oihw && (w_fwd || w_dgrad) && O > 0 && I > 0 && (ksize == 1 || ksize == 3), "bd_pack_conv_weight: bad argument");
-  size_t n = (size_t)O * I * ksize * ksize;
-  pack_weight_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(w_oihw, (__half*)w_fwd, (__half*)w_dgrad, O, I,
-                                                                        ksize * ksize);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -1,0 +1,771 @@
+// tcgen05 (UMMA) implicit-GEMM kernels for sm_100a: TMA-staged, im2col-free, fp16 operands, fp32 TMEM accumulators.
+//
+//   umma_fprop_kernel : D[pixel, n] = sum_{segments} A[pixel + shift, k] * B[n, k]
+//       A = fp16 NHWC activation view, loaded as 4-D TMA boxes {64 ch, bw, bh, bn} (bw*bh*bn = 128 pixels) whose
+//       origin is shifted per filter tap; TMA out-of-bounds zero fill *is* the convolution padding.
+//       B = weights [z][N][K] (K-major) or [z][K][N] (MN-major: dgrad re-uses the forward weights untransposed,
+//       attention re-uses V / K in place).  Serves conv 3x3/1x1 fwd + dgrad, every Linear, QK^T, PV, dP, dQ.
+//   umma_wgrad_kernel : D[m, n] = sum_{pixels} A[pixel, m] * B[pixel + shift, n]   (both operands MN-major)
+//       serves conv/linear weight gradients (split-K, fp32 atomics) and attention dK / dV (batched, fp16 out).
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+// warps 2..5 = epilogue (tcgen05.ld -> bias / temb / residual -> global).  mbarrier ring of kStages stages.
+#include "common.cuh"
+
+#include <cuda.h>
+
+namespace bd {
+void count_launch(int n);
+
+namespace umma {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // fp16 elements per k-block = 128 B = one SWIZZLE_128B row
+constexpr int kMaxSeg = 10;       // 9 taps + fused 1x1 shortcut
+
+struct KSeg {
+  int a_src;   // which A tensor map (0/1)
+  int a_c0;    // first channel in that map
+  int nblk;    // number of 64-wide k-blocks in this run
+  int dx, dy;  // spatial shift of the tile origin
+  int b_src;   // which B tensor map (0/1)
+  int b_k0;    // K coordinate (fprop) in the B map
+  int b_z;     // 3rd coordinate of the B map (tap)
+};
+
+struct FpropParams {
+  int nseg;
+  KSeg seg[kMaxSeg];
+  int total_kblocks;
+  int tiles_w, tiles_h;  // tiles per image
+  int bw, bh, bn;        // pixel box (product 128)
+  int W, H, NB;          // image geometry
+  int HW;                // rows per sample for rowbias
+  int N;                 // output columns
+  int batched;           // B map z += image index (attention)
+  // UMMA smem descriptor fields (16-byte units), host-provided so they can be overridden for bring-up
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+  uint32_t idesc;
+  // epilogue
+  const float* bias;
+  const float* bias2;
+  const float* rowbias;
+  int64_t ld_rowbias;
+  const __half* residual;
+  int64_t ld_res;
+  float scale;
+  void* y;
+  int64_t ld_y;
+  int out_f32;
+  int* error_flag;
+};
+
+struct WgradParams {
+  int pbw, pbh, pbn;        // pixel box of one k-block (product 64)
+  int ptiles_w, ptiles_h;   // k-blocks per image along W / H
+  int kblocks_total;        // all k-blocks (NB/pbn * ptiles_h * ptiles_w), or per image when batched
+  int dx, dy_base;          // unused placeholders
+  int ks;                   // filter size (z = tap -> shift)
+  int n_tiles;              // tiles along N
+  int batched;              // z = image index (attention dK / dV)
+  int splits;
+  int Mtot, Ntot;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo, idesc;
+  void* y;
+  int64_t ld_y;
+  int out_mode;  // 0: fp32 atomicAdd, 1: fp32 store, 2: fp16 store
+  int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 2000000000LL) {  // ~1 s
+      if (error_flag) atomicExch(error_flag, code);
+      return false;
+    }
+  }
+  return true;
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
+         (1ull << 46) | (2ull << 61);
+}
+
+template <int BN, int kStages>
+struct Smem {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 1) * 8 + 16 + 1024 /*alignment slack*/;
+};
+
+// =============================================================================================
+// fprop-style kernel
+// =============================================================================================
+template <int BN, int kStages, bool B_MN>
+__global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                            const __grid_constant__ CUtensorMap tmA1,
+                                                            const __grid_constant__ CUtensorMap tmB0,
+                                                            const __grid_constant__ CUtensorMap tmB1,
+                                                            const FpropParams p) {
+  using L = Smem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+  const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmB1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int s = 0; s < p.nseg && ok; ++s) {
+        const KSeg sg = p.seg[s];
+        const CUtensorMap* mapA = sg.a_src ? &tmA1 : &tmA0;
+        const CUtensorMap* mapB = sg.b_src ? &tmB1 : &tmB0;
+        for (int kb = 0; kb < sg.nblk; ++kb) {
+          ok = mbar_wait(&empty[stage], phase ^ 1, p.error_flag, 1);
+          if (!ok) break;
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full[stage], L::kStageBytes);
+          tma_load_4d(mapA, &full[stage], sa, sg.a_c0 + kb * BK, w0 + sg.dx, h0 + sg.dy, n0);
+          const int bz = sg.b_z + (p.batched ? n0 : 0);
+          if (!B_MN) {
+            tma_load_3d(mapB, &full[stage], sb, sg.b_k0 + kb * BK, n_tile * BN, bz);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              tma_load_3d(mapB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, sg.b_k0 + kb * BK, bz);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int it = 0; it < p.total_kblocks; ++it) {
+        ok = mbar_wait(&full[stage], phase, p.error_flag, 2);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+        const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; ++k) {
+          // K-major: advance 16 elements = 32 B inside the 128B swizzle row; MN-major: 16 k-rows = 2048 B
+          const uint64_t ad = make_desc(sa + k * 32, p.a_lbo, p.a_sbo);
+          const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+          umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+      if (ok) umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w%4) .. +31 =====
+    const int q = warp & 3;
+    const int r = q * 32 + lane;  // row within the tile
+    const int dn = r / (p.bw * p.bh), dh = (r / p.bw) % p.bh, dw = r % p.bw;
+    const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
+    const bool valid = n < p.NB && h < p.H && w < p.W;
+    const int64_t m = ((int64_t)n * p.H + h) * p.W + w;
+    const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
+    tc_fence_after();
+    if (ok) {
+      const float* rb = (p.rowbias && valid) ? p.rowbias + (m / p.HW) * p.ld_rowbias : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+        if (valid) {
+          const int col = n_tile * BN + c0;
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.bias2) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + col + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (rb) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 b4 = *reinterpret_cast<const float4*>(rb + col + j);
+              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
+            }
+          }
+          if (p.residual) {
+            const __half* rr = p.residual + m * p.ld_res + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              float g[8];
+              unpack8(*reinterpret_cast<const half8*>(rr + j), g);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) f[j + k] += g[k];
+            }
+          }
+          if (p.scale != 1.0f) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] *= p.scale;
+          }
+          if (p.out_f32) {
+            float* yr = reinterpret_cast<float*>(p.y) + m * p.ld_y + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+          } else {
+            __half* yr = reinterpret_cast<__half*>(p.y) + m * p.ld_y + col;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) *reinterpret_cast<half8*>(yr + j) = pack8(f + j);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// =============================================================================================
+// wgrad-style kernel: both operands MN-major, K = pixels.  grid (m_tiles*n_tiles, z, splits)
+// =============================================================================================
+template <int BN, int kStages>
+__global__ void __launch_bounds__(192, 1) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB,
+                                                            const WgradParams p) {
+  using L = Smem<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tile = blockIdx.x / p.n_tiles, n_tile = blockIdx.x % p.n_tiles;
+  const int z = blockIdx.y;
+  int dx = 0, dy = 0;
+  if (!p.batched && p.ks == 3) { dy = z / 3 - 1; dx = z % 3 - 1; }
+  const int per = (p.kblocks_total + p.splits - 1) / p.splits;
+  const int kb_begin = blockIdx.z * per;
+  const int kb_end = min(p.kblocks_total, kb_begin + per);
+  const int nk = kb_end - kb_begin;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nk > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
+          if (!mbar_wait(&empty[stage], phase ^ 1, p.error_flag, 1)) break;
+          const int pw = (kb % p.ptiles_w) * p.pbw, ph = ((kb / p.ptiles_w) % p.ptiles_h) * p.pbh;
+          const int pn = p.batched ? z : (kb / (p.ptiles_w * p.ptiles_h)) * p.pbn;
+          uint8_t* sa = smem + stage * L::kStageBytes;
+          uint8_t* sb = sa + L::kABytes;
+          mbar_expect_tx(&full[stage], L::kStageBytes);
+#pragma unroll
+          for (int i = 0; i < BM / 64; ++i)
+            tma_load_4d(&tmA, &full[stage], sa + i * (64 * BK * 2), m_tile * BM + i * 64, pw, ph, pn);
+#pragma unroll
+          for (int i = 0; i < BN / 64; ++i)
+            tma_load_4d(&tmB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, pw + dx, ph + dy, pn);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        bool ok = true;
+        for (int it = 0; it < nk; ++it) {
+          ok = mbar_wait(&full[stage], phase, p.error_flag, 2);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_desc(sa + k * 2048, p.a_lbo, p.a_sbo);
+            const uint64_t bd = make_desc(sb + k * 2048, p.b_lbo, p.b_sbo);
+            umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(tmem_full);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = m_tile * BM + q * 32 + lane;
+      const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
+      tc_fence_after();
+      if (ok) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
+          const int col = n_tile * BN + c0;
+          if (row < p.Mtot && col < p.Ntot) {
+            const int64_t off = ((int64_t)z * p.Mtot + row) * p.ld_y + col;
+            if (p.out_mode == 0) {
+              float* yr = reinterpret_cast<float*>(p.y) + off;
+#pragma unroll
+              for (int j = 0; j < 32; ++j) atomicAdd(yr + j, __uint_as_float(v[j]));
+            } else if (p.out_mode == 1) {
+              float* yr = reinterpret_cast<float*>(p.y) + off;
+#pragma unroll
+              for (int j = 0; j < 32; j += 4)
+                *reinterpret_cast<float4*>(yr + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
+                                                                 __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+              __half* yr = reinterpret_cast<__half*>(p.y) + off;
+              float f[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) *reinterpret_cast<half8*>(yr + j) = pack8(f + j);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+// rank-4 fp16 map: dims {d0,d1,d2,d3} (d0 contiguous), strides in ELEMENTS for d1..d3, box {b0..b3}
+static bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+                     const uint32_t* box) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank - 1; ++i) gs[i] = strides_elems[i] * 2;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): rank %d dims {%llu,%llu,%llu,%llu} box {%u,%u,%u,%u} ptr %p stride1 %llu",
+              (int)r, rank, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)(rank > 2 ? dims[2] : 0),
+              (unsigned long long)(rank > 3 ? dims[3] : 0), box[0], box[1], rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0, ptr,
+              (unsigned long long)gs[0]);
+    return false;
+  }
+  return true;
+}
+
+static int* g_error_flag = nullptr;  // device int, lazily allocated once per process (not per call)
+int* error_flag() {
+  if (!g_error_flag) {
+    cudaMalloc(&g_error_flag, sizeof(int));
+    cudaMemset(g_error_flag, 0, sizeof(int));
+  }
+  return g_error_flag;
+}
+
+static uint32_t env_u32(const char* name, uint32_t dflt) {
+  const char* v = getenv(name);
+  return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
+}
+
+// choose the 128-pixel box for a (H, W) image grid; returns false if the geometry does not tile
+static bool pick_box(int H, int W, int pixels, int* bw, int* bh, int* bn) {
+  if (W >= pixels) {
+    if (W % pixels) return false;
+    *bw = pixels; *bh = 1; *bn = 1;
+    return true;
+  }
+  if (pixels % W) return false;
+  int rows = pixels / W;
+  if (H >= rows) {
+    if (H % rows) return false;
+    *bw = W; *bh = rows; *bn = 1;
+    return true;
+  }
+  if (rows % H) return false;
+  *bw = W; *bh = H; *bn = rows / H;
+  return *bw <= 256 && *bh <= 256 && *bn <= 256;
+}
+
+template <int BN, bool B_MN>
+static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
+                          const FpropParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int kStages = BN == 128 ? 5 : 6;
+  using L = Smem<BN, kStages>;
+  auto kern = umma_fprop_kernel<BN, kStages, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    attr_set = true;
+  }
+  kern<<<grid, 192, L::kTotal, st>>>(a0, a1, b, b1, p);
+  count_launch(1);
+  return 0;
+}
+
+// Generic fprop launch used by conv fwd / dgrad / linear / attention GEMMs.
+//   A: fp16 view (NB, H, W, Ca) with ld_a; optional second source for fused K segments.
+//   B: fp16 [Z][rows][cols] with row length ldb: K-major (rows = N, cols = K) or MN-major (rows = K, cols = N).
+struct FpropCall {
+  const void* a; int64_t ld_a; int Ca;
+  const void* a2; int64_t ld_a2; int Ca2;
+  int NB, H, W;
+  const void* b; int b_rows, b_cols, b_z; int64_t ld_b;   // main weights
+  const void* b2; int64_t ld_b2;   // weights of the fused second segment [N][Ca2] (K-major), nullable
+  int N, ks; bool b_mn; bool batched; bool flip_taps;
+  const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias; int HW_rowbias;
+  const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+};
+
+int fprop_supported(const FpropCall& c) {
+  int bw, bh, bn;
+  if (c.Ca % 64 || (c.a2 && c.Ca2 % 64)) return 0;
+  if (c.N % 64) return 0;
+  if (c.ld_a % 8 || (c.a2 && c.ld_a2 % 8) || c.ld_b % 8) return 0;
+  if (((uintptr_t)c.a & 15) || ((uintptr_t)c.b & 15) || (c.a2 && ((uintptr_t)c.a2 & 15))) return 0;
+  if (!pick_box(c.H, c.W, BM, &bw, &bh, &bn)) return 0;
+  if (c.batched && bn != 1) return 0;
+  if (c.ks != 1 && c.ks != 3) return 0;
+  return 1;
+}
+
+int fprop_launch(const FpropCall& c, cudaStream_t st) {
+  FpropParams p;
+  memset(&p, 0, sizeof(p));
+  if (!pick_box(c.H, c.W, BM, &p.bw, &p.bh, &p.bn)) { set_error("umma fprop: geometry %dx%d does not tile", c.H, c.W); return BD_ERR_UNSUPPORTED; }
+  p.tiles_w = c.W / p.bw;
+  p.tiles_h = c.H / p.bh;
+  p.W = c.W; p.H = c.H; p.NB = c.NB;
+  p.HW = c.HW_rowbias > 0 ? c.HW_rowbias : c.H * c.W;
+  p.N = c.N;
+  p.batched = c.batched ? 1 : 0;
+  const int BN = (c.N % 128 == 0) ? 128 : 64;
+  // K segments
+  int nseg = 0, total = 0;
+  const int taps = c.ks * c.ks;
+  for (int t = 0; t < taps; ++t) {
+    KSeg& s = p.seg[nseg++];
+    s.a_src = 0; s.a_c0 = 0; s.nblk = c.Ca / 64;
+    int r = t / c.ks, q = t % c.ks;
+    s.dy = c.ks == 3 ? r - 1 : 0;
+    s.dx = c.ks == 3 ? q - 1 : 0;
+    if (c.flip_taps) { s.dy = -s.dy; s.dx = -s.dx; }  // dgrad: dX[q] = sum_tap dY[q - off(tap)] W[tap]^T
+    s.b_src = 0; s.b_k0 = 0; s.b_z = t;
+    total += s.nblk;
+  }
+  if (c.a2) {
+    KSeg& s = p.seg[nseg++];
+    s.a_src = 1; s.a_c0 = 0; s.nblk = c.Ca2 / 64; s.dx = s.dy = 0; s.b_src = 1; s.b_k0 = 0; s.b_z = 0;
+    total += s.nblk;
+  }
+  p.nseg = nseg;
+  p.total_kblocks = total;
+  // descriptors
+  p.a_lbo = env_u32("BD_UMMA_AK_LBO", 1);
+  p.a_sbo = env_u32("BD_UMMA_AK_SBO", 64);
+  if (c.b_mn) { p.b_lbo = env_u32("BD_UMMA_BMN_LBO", 512); p.b_sbo = env_u32("BD_UMMA_BMN_SBO", 64); }
+  else        { p.b_lbo = env_u32("BD_UMMA_BK_LBO", 1);   p.b_sbo = env_u32("BD_UMMA_BK_SBO", 64); }
+  p.idesc = (1u << 4) | ((c.b_mn ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  p.bias = c.bias; p.bias2 = c.bias2; p.rowbias = c.rowbias; p.ld_rowbias = c.ld_rowbias;
+  p.residual = (const __half*)c.residual; p.ld_res = c.ld_res; p.scale = c.scale;
+  p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
+  p.error_flag = error_flag();
+
+  CUtensorMap ma0, ma1, mb, mb1;
+  {
+    uint64_t dims[4] = {(uint64_t)c.Ca, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)c.W * c.ld_a, (uint64_t)c.H * c.W * c.ld_a};
+    uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (!make_map(&ma0, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[4] = {(uint64_t)c.Ca2, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a2, (uint64_t)c.W * c.ld_a2, (uint64_t)c.H * c.W * c.ld_a2};
+    uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
+    if (!make_map(&ma1, c.a2, 4, dims, str, box)) return BD_ERR_CUDA;
+  } else {
+    ma1 = ma0;
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)c.b_cols, (uint64_t)c.b_rows, (uint64_t)c.b_z};
+    uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
+    uint32_t box[3] = {64, c.b_mn ? 64u : (uint32_t)BN, 1};
+    if (!make_map(&mb, c.b, 3, dims, str, box)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
+    uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
+    uint32_t box[3] = {64, (uint32_t)BN, 1};
+    if (!make_map(&mb1, c.b2, 3, dims, str, box)) return BD_ERR_CUDA;
+  } else {
+    mb1 = mb;
+  }
+  const int m_tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.bn);
+  dim3 grid(m_tiles, c.N / BN);
+  if (BN == 128) {
+    if (c.b_mn) launch_fprop_t<128, true>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false>(ma0, ma1, mb, mb1, p, grid, st);
+  } else {
+    if (c.b_mn) launch_fprop_t<64, true>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<64, false>(ma0, ma1, mb, mb1, p, grid, st);
+  }
+  return BD_OK;
+}
+
+// wgrad-style launch.  A = "dY" view (NB,H,W,Ma) -> M rows; B = "X" view (NB,H,W,Nb) -> N cols.
+struct WgradCall {
+  const void* a; int64_t ld_a; int Mtot;
+  const void* b; int64_t ld_b; int Ntot;
+  int NB, H, W, ks; bool batched;
+  void* y; int64_t ld_y; int out_mode;  // 0 atomic f32, 1 store f32, 2 store f16
+  int zcount;                            // taps, or batch count
+};
+
+int wgrad_supported(const WgradCall& c) {
+  int bw, bh, bn;
+  if (c.Mtot % 64 || c.Ntot % 64) return 0;
+  if (c.ld_a % 8 || c.ld_b % 8) return 0;
+  if (((uintptr_t)c.a & 15) || ((uintptr_t)c.b & 15)) return 0;
+  if (!pick_box(c.H, c.W, 64, &bw, &bh, &bn)) return 0;
+  if (c.batched && bn != 1) return 0;
+  if (c.ks != 1 && c.ks != 3) return 0;
+  return 1;
+}
+
+template <int BN>
+static int launch_wgrad_t(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, dim3 grid, cudaStream_t st) {
+  constexpr int kStages = BN == 128 ? 5 : 6;
+  using L = Smem<BN, kStages>;
+  auto kern = umma_wgrad_kernel<BN, kStages>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
+    attr_set = true;
+  }
+  kern<<<grid, 192, L::kTotal, st>>>(a, b, p);
+  count_launch(1);
+  return 0;
+}
+
+int wgrad_launch(const WgradCall& c, cudaStream_t st) {
+  WgradParams p;
+  memset(&p, 0, sizeof(p));
+  if (!pick_box(c.H, c.W, 64, &p.pbw, &p.pbh, &p.pbn)) { set_error("umma wgrad: geometry %dx%d does not tile", c.H, c.W); return BD_ERR_UNSUPPORTED; }
+  p.ptiles_w = c.W / p.pbw;
+  p.ptiles_h = c.H / p.pbh;
+  const int per_image = p.ptiles_w * p.ptiles_h;
+  p.kblocks_total = c.batched ? per_image : per_image * ceil_div(c.NB, p.pbn);
+  p.ks = c.ks;
+  p.batched = c.batched ? 1 : 0;
+  p.Mtot = c.Mtot; p.Ntot = c.Ntot;
+  const int BN = (c.Ntot % 128 == 0) ? 128 : 64;
+  p.n_tiles = c.Ntot / BN;
+  const int m_tiles = ceil_div(c.Mtot, BM);
+  const int tiles = m_tiles * p.n_tiles * c.zcount;
+  int splits = 1;
+  if (c.out_mode == 0) {
+    splits = ceil_div(num_sms(), tiles);
+    int maxs = p.kblocks_total / 8 > 0 ? p.kblocks_total / 8 : 1;  // >= 8 k-blocks per CTA
+    if (splits > maxs) splits = maxs;
+    if (splits < 1) splits = 1;
+  }
+  p.splits = splits;
+  p.a_lbo = env_u32("BD_UMMA_AMN_LBO", 512);
+  p.a_sbo = env_u32("BD_UMMA_AMN_SBO", 64);
+  p.b_lbo = env_u32("BD_UMMA_BMN_LBO", 512);
+  p.b_sbo = env_u32("BD_UMMA_BMN_SBO", 64);
+  p.idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+  p.y = c.y; p.ld_y = c.ld_y; p.out_mode = c.out_mode;
+  p.error_flag = error_flag();
+  CUtensorMap ma, mb;
+  uint32_t box[4] = {64, (uint32_t)p.pbw, (uint32_t)p.pbh, (uint32_t)p.pbn};
+  {
+    uint64_t dims[4] = {(uint64_t)c.Mtot, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)c.W * c.ld_a, (uint64_t)c.H * c.W * c.ld_a};
+    if (!make_map(&ma, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)c.Ntot, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_b, (uint64_t)c.W * c.ld_b, (uint64_t)c.H * c.W * c.ld_b};
+    if (!make_map(&mb, c.b, 4, dims, str, box)) return BD_ERR_CUDA;
+  }
+  dim3 grid(m_tiles * p.n_tiles, c.zcount, splits);
+  if (BN == 128) launch_wgrad_t<128>(ma, mb, p, grid, st); else launch_wgrad_t<64>(ma, mb, p, grid, st);
+  return BD_OK;
+}
+
+int read_error_flag() {
+  int v = 0;
+  if (g_error_flag) {
+    cudaMemcpy(&v, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost);
+    if (v) cudaMemset(g_error_flag, 0, sizeof(int));
+  }
+  return v;
+}
+
+}  // namespace umma
+}  // namespace bd

@@ -32,7 +32,12 @@ extern "C" {
 #define BD_ERR_UNSUPPORTED (-3) /* valid request this build cannot serve (NotImplementedError)       */
 
 int bd_version(void);
+/* one-time per-process/device setup (allocates the 4-byte device error word used by the tcgen05 kernels'
+ * bounded mbarrier waits).  Must be called once before any CUDA-graph capture. */
+int bd_init(void);
 const char* bd_last_error(void);
+/* non-zero if a tcgen05 kernel reported a pipeline time-out since the last call (synchronises; debug/tests) */
+int bd_umma_error(void);
 /* 1 if the current device is compute capability 10.x (tcgen05/TMEM/TMA paths usable) */
 int bd_device_supported(void);
 /* kernel launches issued by this library in this process (bench.py's `gpu_launches`) */
@@ -123,10 +128,12 @@ typedef struct bd_conv_args {
   /* geometry: input (B,H,W,Cin) -> output (B,Ho,Wo,Cout); ksize 1 or 3 */
   int B, H, W, Cin, Cout, ksize, mode, pad; /* pad: only for BD_CONV_S2_PAD01: 0 -> (0,1,0,1), 1 -> symmetric 1 */
   const void* x;  int64_t ld_x;     /* f16 NHWC view                                         */
-  const void* w;                    /* packed f16 [tap][Cout][Cin] (bd_pack_conv_weight)     */
+  const void* w;                    /* packed f16 [tap][Cout][Cin] (the native layout of the flat
+                                       parameter buffer; fwd AND dgrad read it untransposed)  */
   /* optional second K segment fused into the same accumulation (1x1 shortcut, resnet.py:596-597): */
   const void* x2; int64_t ld_x2; int Cin2; const void* w2; /* w2 packed [1][Cout][Cin2]      */
   const float* bias;                /* (Cout) f32, nullable                                  */
+  const float* bias2;               /* second bias (the fused shortcut's), nullable          */
   const float* rowbias; int64_t ld_rowbias; /* (B, Cout) f32 added per sample (temb), nullable */
   const void* residual; int64_t ld_res;     /* f16 NHWC view added in the epilogue, nullable */
   float out_scale;                  /* multiplies the result (1/output_scale_factor)          */
@@ -135,29 +142,38 @@ typedef struct bd_conv_args {
 } bd_conv_args;
 
 int bd_conv_fwd(const bd_conv_args* a, void* stream);
-/* dgrad: dx (B,H,W,Cin) = conv^T(dy (B,Ho,Wo,Cout)); w_t is the packed transposed weight [tap][Cin][Cout].
- * `residual` is added (gradient fan-in), x2/w2 unused.  Uses the same struct: x:=dy, y:=dx, Cin/Cout keep
- * their FORWARD meaning.                                                                               */
+/* dgrad: dx (B,H,W,Cin) = conv^T(dy (B,Ho,Wo,Cout)) with the SAME packed forward weight (read as an
+ * MN-major operand).  `residual` is added (gradient fan-in), x2/w2 unused.  Uses the same struct:
+ * x:=dy, y:=dx, Cin/Cout keep their FORWARD meaning.                                                    */
 int bd_conv_dgrad(const bd_conv_args* a, void* stream);
-/* wgrad: dw f32 in the master layout OIHW (Cout,Cin,k,k) += sum over pixels; dbias (Cout) f32.
- * x (B,H,W,Cin) f16 view, dy (B,Ho,Wo,Cout) f16 view.  `work`: bd_conv_wgrad_workspace_bytes bytes.   */
-size_t bd_conv_wgrad_workspace_bytes(int Cin, int Cout, int ksize);
-int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, float* dw, float* dbias, void* work,
+/* wgrad: dw f32 in the packed layout [tap][Cout][Cin] (+)= sum over pixels (split-K, fp32 atomics);
+ * dbias (Cout) f32 nullable.  x (B,H,W,Cin) f16 view, dy (B,Ho,Wo,Cout) f16 view.                      */
+int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, float* dw, float* dbias,
                   int B, int H, int W, int Cin, int Cout, int ksize, int mode, int pad, int accumulate, int impl,
                   void* stream);
 
-/* OIHW f32 master weight -> f16 [tap][O][I] (fwd B operand) and/or [tap][I][O] (dgrad B operand). */
-int bd_pack_conv_weight(const float* w_oihw, void* w_fwd, void* w_dgrad, int O, int I, int ksize, void* stream);
+/* torch OIHW f32 weight -> packed [tap][O][I] as f32 and/or f16 (load_state_dict of foreign checkpoints, tests) */
+int bd_pack_conv_weight(const float* w_oihw, float* w_packed_f32, void* w_packed_f16, int O, int I, int ksize, void* stream);
+/* f32 -> f16 copy of the flat parameter buffer (one launch per optimizer step) */
+int bd_cast_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
+/* out[b][c] (+)= sum over the rows of sample b of x (f16 view): per-sample temb gradients and bias gradients */
+int bd_colsum_f16(const void* x, int64_t ld_x, float* out, int64_t ld_out, int B, int64_t rows_per_b, int C,
+                  int accumulate, void* stream);
+/* dx = dy * silu'(x) (f32), n elements: backward of the SiLUs in the timestep MLP */
+int bd_silu_bwd_f32(const float* dy, const float* x, float* dx, size_t n, void* stream);
+/* y_f16 = silu(x_f32) */
+int bd_silu_f32_to_f16(const float* x, void* y, size_t n, void* stream);
 
-/* conv_in (Cin=3, f32 NCHW image in -> f16 NHWC out), unet_2d.py:124,283 */
-int bd_conv_in_fwd(const float* x_nchw, const float* w_oihw, const float* bias, void* y, int64_t ld_y, int B, int Cin,
+/* conv_in (Cin=3, f32 NCHW image in -> f16 NHWC out), unet_2d.py:124,283.  Weights / weight gradients
+ * of these two layers are f32 in the packed [tap][Cout][Cin] layout.                                  */
+int bd_conv_in_fwd(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, int B, int Cin,
                    int H, int W, int Cout, void* stream);
 int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* dw, float* dbias, int B, int Cin,
                      int H, int W, int Cout, int accumulate, void* stream);
 /* conv_out (f16 NHWC in -> Cout=3 f32 NCHW eps_hat), unet_2d.py:217,314; and its backward */
-int bd_conv_out_fwd(const void* x, int64_t ld_x, const float* w_oihw, const float* bias, float* y_nchw, int B, int Cin,
+int bd_conv_out_fwd(const void* x, int64_t ld_x, const float* w_packed, const float* bias, float* y_nchw, int B, int Cin,
                     int H, int W, int Cout, void* stream);
-int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_oihw, const float* dy_nchw, void* dx, int64_t ld_dx,
+int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const float* dy_nchw, void* dx, int64_t ld_dx,
                     float* dw, float* dbias, int B, int Cin, int H, int W, int Cout, int accumulate, void* stream);
 
 /* K9  F.interpolate(scale_factor=2, nearest) (D/models/resnet.py:146) and its adjoint (2x2 sum) */
@@ -172,8 +188,9 @@ int bd_add_f16(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* y
  * qkv: (B, S, 3C) f16 with ld; heads split C as in reshape_heads_to_batch_dim (:77-82).
  * probs (B*heads, S, S) f16 is saved for backward (nullable in inference).  out: (B,S,C) f16 view.
  * ---------------------------------------------------------------------------------------------- */
-int bd_attention_fwd(const void* qkv, int64_t ld_qkv, void* probs, void* out, int64_t ld_out, int B, int S, int C,
-                     int heads, float scale, int impl, void* stream);
+size_t bd_attention_fwd_workspace_bytes(int B, int S, int C, int heads);
+int bd_attention_fwd(const void* qkv, int64_t ld_qkv, void* probs, void* out, int64_t ld_out, void* work, int B, int S,
+                     int C, int heads, float scale, int impl, void* stream);
 /* d_qkv (B,S,3C) from d_out; needs probs and qkv from forward. */
 int bd_attention_bwd(const void* qkv, int64_t ld_qkv, const void* probs, const void* d_out, int64_t ld_dout,
                      void* d_qkv, int64_t ld_dqkv, void* work, int B, int S, int C, int heads, float scale, int impl,

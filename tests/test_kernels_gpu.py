@@ -1,0 +1,449 @@
+"""Kernel-level parity (GPU).  Every CUDA kernel is called through the C-ABI and compared with
+  * the committed reference fixtures (bit-exact for the scheduler / batch-prep arithmetic), or
+  * a plain PyTorch fp32 evaluation of the same op on the same fp16-rounded inputs (tolerances stated per test).
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+T = torch.from_numpy
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from baddiffusion_b200 import ops as o
+
+    o.L.lib()
+    return o
+
+
+def dev(x):
+    return x.cuda()
+
+
+def nhwc_half(x_nchw):
+    """fp32 NCHW -> fp16 NHWC contiguous (B,H,W,C) + the fp16-rounded fp32 NCHW copy used by the torch reference."""
+    h = x_nchw.half()
+    return h.permute(0, 2, 3, 1).contiguous(), h.float()
+
+
+def to_nchw(y_nhwc):
+    return y_nhwc.float().permute(0, 3, 1, 2)
+
+
+def packed(w_oihw):
+    """OIHW fp32 -> packed fp16 [tap][O][I] and the fp16-rounded OIHW fp32 copy."""
+    h = w_oihw.half()
+    O, I, k, _ = w_oihw.shape
+    return h.permute(2, 3, 0, 1).reshape(k * k, O, I).contiguous(), h.float()
+
+
+def rel_err(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+# ------------------------------------------------------------------------------------------------
+# bit-exact arithmetic vs. the reference fixtures
+# ------------------------------------------------------------------------------------------------
+def test_batch_prep_bit_exact(ops, golden):
+    g = golden("q_sample")
+    bt = golden("backdoor_tensors")
+    img, t, noise = dev(T(g["image"])), dev(T(g["t"])), dev(T(g["noise"]))
+    isp = dev(T(g["is_poison"]).to(torch.uint8))
+    trig, targ = dev(T(bt["trigger_BOX_14_32"])), dev(T(bt["target_HAT_32"]))
+    alphas, acp = dev(T(g["alphas"])), dev(T(g["alphas_cumprod"]))
+    xn, tg = ops.batch_prep(img, isp, trig, targ, t, alphas, acp, noise=noise)
+    assert torch.equal(xn.cpu(), T(g["x_noisy"]))
+    assert torch.equal(tg.cpu(), T(g["target"]))
+    # explicit-R form (the signature of loss.q_sample_diffuser)
+    xn2, tg2 = ops.batch_prep(dev(T(g["x0"])), None, None, None, t, alphas, acp, noise=noise, R=dev(T(g["R"])))
+    assert torch.equal(xn2.cpu(), T(g["x_noisy"])) and torch.equal(tg2.cpu(), T(g["target"]))
+    # Philox noise: statistics only
+    big = torch.zeros(64, 3, 32, 32, device="cuda")
+    no = torch.empty_like(big)
+    tt = torch.zeros(64, dtype=torch.int64, device="cuda")
+    ops.batch_prep(big, None, None, None, tt, alphas, acp, noise=None, seed=123, offset=7, noise_out=no)
+    assert abs(float(no.mean())) < 0.02 and abs(float(no.std()) - 1.0) < 0.02
+    no2 = torch.empty_like(big)
+    ops.batch_prep(big, None, None, None, tt, alphas, acp, noise=None, seed=123, offset=8, noise_out=no2)
+    assert not torch.equal(no, no2)
+
+
+def _ddpm_coef(acp, t, nsteps, vt, clip, clip_def=0.0):
+    """host-side scalars with the reference's own 0-d fp32 torch expressions (scheduling_ddpm.py:352-411)."""
+    from baddiffusion_b200.schedulers import ddpm_coef_row
+
+    return ddpm_coef_row(acp, t, nsteps, 1000, vt, clip, 1.0, clip_def)
+
+
+def test_scheduler_steps_bit_exact(ops, golden):
+    from baddiffusion_b200.schedulers import ddim_coef_row, ddpm_coef_row
+    from oracle import torch_ref as O
+
+    g = golden("scheduler_steps")
+    _, _, acp = O.beta_tables()
+    x, eps = dev(T(g["x"])), dev(T(g["eps"]))
+    z = dev(torch.randn(x.shape, generator=torch.Generator().manual_seed(11)))
+    n = 0
+    for key, val in g.items():
+        out = torch.empty_like(x)
+        if key.startswith("ddpm_fixed"):
+            _, _, vt2, clip, nsteps, t = key.split("_")
+            row = ddpm_coef_row(acp, int(t), int(nsteps), 1000, "fixed_" + vt2, bool(int(clip)), 1.0, 0.0)
+            ops.ddpm_step(x, eps, z, out, dev(row))
+        elif key == "ddpm_clipdef_500":
+            row = ddpm_coef_row(acp, 500, 1000, 1000, "fixed_small", False, 1.0, 1.0)
+            ops.ddpm_step(x, eps, z, out, dev(row))
+        elif key.startswith("ddim_"):
+            _, clip, nsteps, t, eta = key.split("_")
+            row = ddim_coef_row(acp, int(t), int(nsteps), 1000, float(eta[3:]), bool(int(clip)), 1.0, True, False)
+            ops.ddim_step(x, eps, z, out, dev(row))
+        else:
+            continue
+        assert torch.equal(out.cpu(), T(val)), key
+        n += 1
+    assert n >= 40
+
+
+def test_finalize_images(ops):
+    x = torch.randn(5, 3, 32, 32, device="cuda") * 1.5
+    o01 = torch.empty(5, 32, 32, 3, device="cuda")
+    ou8 = torch.empty(5, 32, 32, 3, dtype=torch.uint8, device="cuda")
+    ops.finalize_images(x, o01, ou8)
+    ref = (x / 2 + 0.5).clamp(0, 1).permute(0, 2, 3, 1)
+    assert torch.equal(o01, ref.contiguous())
+    assert np.array_equal(ou8.cpu().numpy(), (ref.cpu().numpy() * 255).round().astype("uint8"))
+
+
+def test_mse(ops):
+    a, b = torch.randn(8, 3, 32, 32, device="cuda"), torch.randn(8, 3, 32, 32, device="cuda")
+    loss = torch.zeros(1, device="cuda")
+    grad = torch.empty_like(a)
+    part = torch.empty(1024, device="cuda")
+    scale = torch.tensor([4096.0], device="cuda")
+    ops.mse_fwd_bwd(a, b, loss, grad, part, scale)
+    ref = F.mse_loss(b.double(), a.double())
+    assert abs(float(loss) - float(ref)) < 1e-6 * float(ref)
+    assert torch.allclose(grad, 4096.0 * 2 * (a - b) / a.numel(), rtol=1e-6, atol=0)
+
+
+# ------------------------------------------------------------------------------------------------
+# GroupNorm (+SiLU)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,C,H,silu", [(3, 128, 32, True), (2, 384, 16, True), (5, 256, 4, False), (2, 32, 32, True),
+                                        (2, 96, 16, True)])
+def test_groupnorm_fwd_bwd(ops, B, C, H, silu):
+    torch.manual_seed(0)
+    G, eps = 32, 1e-6
+    x32 = torch.randn(B, C, H, H, device="cuda") * 2 + 0.5
+    x, xr = nhwc_half(x32)
+    gamma = torch.randn(C, device="cuda") * 0.2 + 1
+    beta = torch.randn(C, device="cuda") * 0.2
+    y = torch.empty_like(x)
+    stats = torch.empty(B, G, 2, device="cuda")
+    work = torch.empty(ops.gn_workspace_floats(B, C), device="cuda")
+    ops.groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, silu)
+    xr = xr.requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.group_norm(xr, G, gr, br, eps)
+    ref = F.silu(ref) if silu else ref
+    # fp16 output rounding: 2^-11 relative
+    assert (to_nchw(y) - ref).abs().max() < 2e-3 * max(1.0, float(ref.abs().max()))
+    dy32 = torch.randn_like(ref)
+    dy, dyr = nhwc_half(dy32)
+    add32 = torch.randn_like(ref)
+    add, addr = nhwc_half(add32)
+    ref.backward(dyr)
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dg, db, work, G, silu, add_dx=add)
+    assert (to_nchw(dx) - (xr.grad + addr)).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
+    assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution: fwd / dgrad / wgrad, CUDA-core and tcgen05 paths
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [  # B, H, Cin, Cout, k
+    (2, 32, 128, 128, 3), (3, 16, 256, 256, 3), (4, 8, 256, 256, 3), (16, 4, 512, 256, 3), (5, 4, 256, 256, 3),
+    (2, 32, 384, 128, 1), (2, 16, 128, 256, 3), (1, 64, 64, 64, 3),
+]
+
+
+def _conv_inputs(B, H, Cin, Cout, k, seed=0):
+    torch.manual_seed(seed)
+    x32 = torch.randn(B, Cin, H, H, device="cuda")
+    w32 = torch.randn(Cout, Cin, k, k, device="cuda") / math.sqrt(Cin * k * k)
+    x, xr = nhwc_half(x32)
+    w, wr = packed(w32)
+    return x, xr, w, wr
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
+def test_conv_fwd(ops, impl, B, H, Cin, Cout, k):
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
+    bias = torch.randn(Cout, device="cuda")
+    rowbias = torch.randn(B, Cout, device="cuda")
+    res32 = torch.randn(B, Cout, H, H, device="cuda")
+    res, resr = nhwc_half(res32)
+    y = torch.empty(B, H, H, Cout, dtype=torch.half, device="cuda")
+    ops.conv_fwd(x, w, y, ksize=k, bias=bias, rowbias=rowbias, residual=res, scale=0.5, impl=im)
+    assert ops.umma_error() == 0
+    ref = (F.conv2d(xr, wr, bias, padding=k // 2) + rowbias[:, :, None, None] + resr) * 0.5
+    err = (to_nchw(y) - ref).abs().max()
+    assert err < 3e-3 * max(1.0, float(ref.abs().max())), float(err)
+    # plain fp32 output, no epilogue extras
+    y32 = torch.empty(B, H, H, Cout, dtype=torch.float32, device="cuda")
+    ops.conv_fwd(x, w, y32, ksize=k, impl=im)
+    ref = F.conv2d(xr, wr, None, padding=k // 2)
+    assert (to_nchw(y32) - ref).abs().max() < 1e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+def test_conv_fwd_fused_shortcut_and_views(ops, impl):
+    """conv2 (3x3 over h) + conv_shortcut (1x1 over the concat input) in one accumulation; inputs and output are
+    channel slices of wider buffers (the zero-copy torch.cat)."""
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    B, H, C1, C2, Cout = 2, 16, 256, 512, 256
+    torch.manual_seed(1)
+    hbuf = torch.randn(B, H, H, C1 + 64, device="cuda").half()
+    xbuf = torch.randn(B, H, H, C2 + 128, device="cuda").half()
+    h, x2 = hbuf[..., 64:], xbuf[..., :C2]
+    w32 = torch.randn(Cout, C1, 3, 3, device="cuda") / math.sqrt(C1 * 9)
+    ws32 = torch.randn(Cout, C2, 1, 1, device="cuda") / math.sqrt(C2)
+    w, wr = packed(w32)
+    ws, wsr = packed(ws32)
+    b1, b2 = torch.randn(Cout, device="cuda"), torch.randn(Cout, device="cuda")
+    ybuf = torch.zeros(B, H, H, Cout + 128, dtype=torch.half, device="cuda")
+    y = ybuf[..., 128:]
+    ops.conv_fwd(h, w, y, ksize=3, bias=b1, bias2=b2, x2=x2, w2=ws, impl=im)
+    assert ops.umma_error() == 0
+    ref = F.conv2d(to_nchw(h), wr, b1, padding=1) + F.conv2d(to_nchw(x2), wsr, b2)
+    assert (to_nchw(y) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+    assert float(ybuf[..., :128].abs().max()) == 0.0  # neighbours of the slice untouched
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
+def test_conv_dgrad(ops, impl, B, H, Cin, Cout, k):
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
+    dy32 = torch.randn(B, Cout, H, H, device="cuda")
+    dy, dyr = nhwc_half(dy32)
+    add32 = torch.randn(B, Cin, H, H, device="cuda")
+    add, addr = nhwc_half(add32)
+    dx = torch.empty(B, H, H, Cin, dtype=torch.half, device="cuda")
+    ops.conv_dgrad(dy, w, dx, ksize=k, residual=add, impl=im)
+    assert ops.umma_error() == 0
+    ref = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, padding=k // 2) + addr
+    assert (to_nchw(dx) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
+def test_conv_wgrad(ops, impl, B, H, Cin, Cout, k):
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
+    dy32 = torch.randn(B, Cout, H, H, device="cuda")
+    dy, dyr = nhwc_half(dy32)
+    dw = torch.full((k * k, Cout, Cin), 7.0, device="cuda")
+    db = torch.full((Cout,), 7.0, device="cuda")
+    ops.conv_wgrad(x, dy, dw, db, ksize=k, impl=im)
+    assert ops.umma_error() == 0
+    ref = torch.nn.grad.conv2d_weight(xr, wr.shape, dyr, padding=k // 2)  # OIHW
+    refp = ref.permute(2, 3, 0, 1).reshape(k * k, Cout, Cin)
+    assert rel_err(dw, refp) < 2e-3
+    assert rel_err(db, dyr.sum((0, 2, 3))) < 2e-3
+    ops.conv_wgrad(x, dy, dw, db, ksize=k, accumulate=True, impl=im)
+    assert rel_err(dw, 2 * refp) < 2e-3
+
+
+@pytest.mark.parametrize("pad", [0, 1])
+def test_conv_stride2(ops, pad):
+    """Downsample2D (resnet.py:199-208): padding=0 -> F.pad(0,1,0,1) first."""
+    B, H, Cc = 3, 16, 128
+    x, xr, w, wr = _conv_inputs(B, H, Cc, Cc, 3)
+    bias = torch.randn(Cc, device="cuda")
+    y = torch.empty(B, H // 2, H // 2, Cc, dtype=torch.half, device="cuda")
+    ops.conv_fwd(x, w, y, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad, bias=bias)
+    xin = xr.clone().requires_grad_(True)
+    wq = wr.clone().requires_grad_(True)
+    xp = F.pad(xin, (0, 1, 0, 1)) if pad == 0 else xin
+    ref = F.conv2d(xp, wq, bias, stride=2, padding=pad)
+    assert ref.shape[-1] == H // 2
+    assert (to_nchw(y) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+    dy32 = torch.randn_like(ref)
+    dy, dyr = nhwc_half(dy32)
+    ref.backward(dyr)
+    dx = torch.empty_like(x)
+    ops.conv_dgrad(dy, w, dx, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad)
+    assert (to_nchw(dx) - xin.grad).abs().max() < 3e-3 * max(1.0, float(xin.grad.abs().max()))
+    dw = torch.empty(9, Cc, Cc, device="cuda")
+    db = torch.empty(Cc, device="cuda")
+    ops.conv_wgrad(x, dy, dw, db, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad)
+    assert rel_err(dw, wq.grad.permute(2, 3, 0, 1).reshape(9, Cc, Cc)) < 2e-3
+
+
+def test_conv_in_out(ops):
+    B, H, Cc = 3, 32, 128
+    torch.manual_seed(0)
+    x = torch.randn(B, 3, H, H, device="cuda")
+    w_in = torch.randn(Cc, 3, 3, 3, device="cuda") / 5
+    b_in = torch.randn(Cc, device="cuda")
+    wp = w_in.permute(2, 3, 0, 1).reshape(9, Cc, 3).contiguous()
+    y = torch.empty(B, H, H, Cc, dtype=torch.half, device="cuda")
+    ops.conv_in_fwd(x, wp, b_in, y)
+    ref = F.conv2d(x, w_in, b_in, padding=1)
+    assert (to_nchw(y) - ref).abs().max() < 2e-3 * max(1.0, float(ref.abs().max()))
+    dy32 = torch.randn_like(ref)
+    dy, dyr = nhwc_half(dy32)
+    dw, db = torch.empty(9, Cc, 3, device="cuda"), torch.empty(Cc, device="cuda")
+    ops.conv_in_wgrad(x, dy, dw, db)
+    refw = torch.nn.grad.conv2d_weight(x, w_in.shape, dyr, padding=1).permute(2, 3, 0, 1).reshape(9, Cc, 3)
+    assert rel_err(dw, refw) < 1e-4 and rel_err(db, dyr.sum((0, 2, 3))) < 1e-4
+    # conv_out
+    h32 = torch.randn(B, Cc, H, H, device="cuda")
+    h, hr = nhwc_half(h32)
+    w_out = torch.randn(3, Cc, 3, 3, device="cuda") / 30
+    b_out = torch.randn(3, device="cuda")
+    wop = w_out.permute(2, 3, 0, 1).reshape(9, 3, Cc).contiguous()
+    e = torch.empty(B, 3, H, H, device="cuda")
+    ops.conv_out_fwd(h, wop, b_out, e)
+    hq = hr.clone().requires_grad_(True)
+    wq = w_out.clone().requires_grad_(True)
+    ref = F.conv2d(hq, wq, b_out, padding=1)
+    assert (e - ref).abs().max() < 1e-4 * max(1.0, float(ref.abs().max()))
+    de = torch.randn_like(ref)
+    ref.backward(de)
+    dh = torch.empty_like(h)
+    dwo, dbo = torch.empty(9, 3, Cc, device="cuda"), torch.empty(3, device="cuda")
+    ops.conv_out_bwd(h, wop, de, dh, dwo, dbo)
+    assert (to_nchw(dh) - hq.grad).abs().max() < 2e-3 * max(1.0, float(hq.grad.abs().max()))
+    assert rel_err(dwo, wq.grad.permute(2, 3, 0, 1).reshape(9, 3, Cc)) < 1e-4
+    assert rel_err(dbo, de.sum((0, 2, 3))) < 1e-4
+
+
+def test_upsample_add_colsum(ops):
+    B, H, Cc = 2, 8, 256
+    x32 = torch.randn(B, Cc, H, H, device="cuda")
+    x, xr = nhwc_half(x32)
+    y = torch.empty(B, 2 * H, 2 * H, Cc, dtype=torch.half, device="cuda")
+    ops.upsample2x(x, y)
+    assert torch.equal(to_nchw(y), F.interpolate(xr, scale_factor=2.0, mode="nearest"))
+    dx = torch.empty_like(x)
+    ops.upsample2x_bwd(y, dx)
+    assert (to_nchw(dx) - 4 * xr).abs().max() < 4e-3 * float(xr.abs().max()) * 4
+    z = torch.empty_like(x)
+    ops.add_f16(x, x, z)
+    assert torch.equal(z.float(), (2 * x.float()).half().float())
+    out = torch.empty(B, Cc, device="cuda")
+    ops.colsum_f16(x.view(B, H * H, Cc), out, H * H, B)
+    assert rel_err(out, xr.sum((2, 3))) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------
+# attention
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl,B,S,C,heads", [("simt", 3, 64, 64, 8), ("simt", 2, 16, 256, 1), ("simt", 2, 256, 256, 1),
+                                              ("umma", 3, 256, 256, 1), ("umma", 2, 256, 512, 1), ("umma", 1, 128, 64, 1)])
+def test_attention_fwd_bwd(ops, impl, B, S, C, heads):
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    torch.manual_seed(0)
+    d = C // heads
+    scale = 1 / math.sqrt(d)
+    qkv = (torch.randn(B, S, 3 * C, device="cuda") * 0.7).half()
+    probs = torch.empty(B * heads, S, S, dtype=torch.half, device="cuda")
+    out = torch.empty(B, S, C, dtype=torch.half, device="cuda")
+    work = torch.empty(ops.L.load().bd_attention_bwd_workspace_bytes(B, S, C, heads), dtype=torch.uint8, device="cuda")
+    ops.attention_fwd(qkv, probs, out, work, B, S, C, heads, scale, impl=im)
+    assert ops.umma_error() == 0
+    q32 = qkv.float().requires_grad_(True)
+    q, k, v = q32[..., :C], q32[..., C:2 * C], q32[..., 2 * C:]
+    sp = lambda z: z.reshape(B, S, heads, d).permute(0, 2, 1, 3).reshape(B * heads, S, d)
+    p = torch.softmax(torch.bmm(sp(q), sp(k).transpose(1, 2)) * scale, dim=-1)
+    o = torch.bmm(p, sp(v)).reshape(B, heads, S, d).permute(0, 2, 1, 3).reshape(B, S, C)
+    assert (probs.float() - p).abs().max() < 2e-3
+    assert (out.float() - o).abs().max() < 4e-3 * max(1.0, float(o.abs().max()))
+    do = torch.randn(B, S, C, device="cuda").half()
+    o.backward(do.float())
+    dqkv = torch.empty_like(qkv)
+    ops.attention_bwd(qkv, probs, do, dqkv, work, B, S, C, heads, scale, impl=im)
+    assert ops.umma_error() == 0
+    assert (dqkv.float() - q32.grad).abs().max() < 6e-3 * max(1.0, float(q32.grad.abs().max()))
+
+
+# ------------------------------------------------------------------------------------------------
+# timestep embedding MLP, small GEMM, optimizer
+# ------------------------------------------------------------------------------------------------
+def test_temb_mlp(ops):
+    from oracle import torch_ref as O
+
+    B, dim, temb = 7, 128, 512
+    torch.manual_seed(0)
+    t = torch.tensor([0, 1, 37, 250, 500, 998, 999], device="cuda")
+    w1, b1 = torch.randn(temb, dim, device="cuda") / 11, torch.randn(temb, device="cuda") / 10
+    w2, b2 = torch.randn(temb, temb, device="cuda") / 22, torch.randn(temb, device="cuda") / 10
+    emb = torch.empty(B, temb, device="cuda")
+    se = torch.empty(B, temb, dtype=torch.half, device="cuda")
+    sin_out, h1 = torch.empty(B, dim, device="cuda"), torch.empty(B, temb, device="cuda")
+    for flip, shift in ((False, 1.0), (True, 0.0)):
+        ops.temb_mlp(t, w1, b1, w2, b2, emb, se, sin_out, h1, flip=flip, freq_shift=shift)
+        ref_sin = O.timestep_embedding(t.cpu(), dim, flip, shift).cuda()
+        assert (sin_out - ref_sin).abs().max() < 2e-5  # sinf/cosf of arguments up to 1e3
+        ref_h1 = F.linear(ref_sin, w1, b1)
+        ref = F.linear(F.silu(ref_h1), w2, b2)
+        assert (h1 - ref_h1).abs().max() < 1e-4 and (emb - ref).abs().max() < 1e-4
+        assert (se.float() - F.silu(ref)).abs().max() < 2e-3
+
+
+def test_sgemm(ops):
+    torch.manual_seed(0)
+    M, N, K = 70, 130, 45
+    A, Bm, bias = torch.randn(M, K, device="cuda"), torch.randn(K, N, device="cuda"), torch.randn(N, device="cuda")
+    Cm = torch.empty(M, N, device="cuda")
+    ops.sgemm(A, K, 1, Bm, N, 1, Cm, N, 1, M, N, K, bias=bias)
+    assert torch.allclose(Cm, A @ Bm + bias, atol=1e-4)
+    # transposed operands + accumulate + silu on A
+    Ct = torch.ones(N, M, device="cuda")
+    ops.sgemm(A, K, 1, Bm, N, 1, Ct, 1, M, M, N, K, accumulate=True, act_silu_a=True)
+    assert torch.allclose(Ct, (F.silu(A) @ Bm).t() + 1, atol=1e-4)
+
+
+def test_adam_matches_torch(ops):
+    torch.manual_seed(0)
+    n = 100_003
+    p0 = torch.randn(n, device="cuda")
+    p = p0.clone()
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    tp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([tp], lr=2e-4)
+    state = torch.tensor([1024.0, 0, 0, 0, 0], device="cuda")
+    step = torch.zeros(1, dtype=torch.int32, device="cuda")
+    lr = torch.tensor([2e-4], device="cuda")
+    part = torch.empty(1024, device="cuda")
+    for i in range(5):
+        g = torch.randn(n, device="cuda") * (3.0 if i % 2 else 0.001)
+        tp.grad = g.clone()
+        torch.nn.utils.clip_grad_norm_([tp], 1.0)
+        opt.step()
+        gs = g * 1024.0
+        ops.grad_norm(gs, part, state)
+        ops.adam_step(p, gs, m, v, lr, step, state)
+        ops.scaler_update(state, step)
+        assert abs(float(state[3]) - float(g.norm())) < 1e-4 * float(g.norm())
+    assert int(step) == 5
+    assert (p - tp.data).abs().max() < 2e-6
+    # overflow: step skipped, scale halved
+    gs = torch.full((n,), float("inf"), device="cuda")
+    before = p.clone()
+    ops.grad_norm(gs, part, state)
+    ops.adam_step(p, gs, m, v, lr, step, state)
+    ops.scaler_update(state, step)
+    assert torch.equal(p, before) and float(state[0]) == 512.0 and int(step) == 5
