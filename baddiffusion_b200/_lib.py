@@ -43,21 +43,21 @@ _SIGS = {
     "bd_umma_error": (i32, []),
     "bd_device_supported": (i32, []),
     "bd_launch_count": (u64, []),
-    "bd_batch_prep": (i32, [vp] * 12 + [i32] * 5 + [u64, u64, vp]),
+    "bd_batch_prep": (i32, [vp] * 12 + [i32] * 5 + [u64, u64, vp, vp]),
     "bd_mse_workspace_floats": (sz, []),
     "bd_mse_fwd_bwd": (i32, [vp] * 6 + [sz, vp]),
     "bd_ddpm_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),
     "bd_ddim_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),
     "bd_sampler_advance": (i32, [vp, vp, vp, i32, i32, vp]),
     "bd_finalize_images": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
-    "bd_temb_mlp": (i32, [vp] * 9 + [i32, i32, i32, i32, f32, vp]),
+    "bd_temb_mlp": (i32, [vp] * 9 + [i32, i32, i32, i32, vp, vp]),
     "bd_sgemm": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_gn_workspace_floats": (sz, [i32, i32]),
     "bd_groupnorm_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "bd_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_dgrad": (i32, [C.POINTER(ConvArgs), vp]),
-    "bd_conv_wgrad": (i32, [vp, i64, vp, i64, vp, vp] + [i32] * 11 + [vp]),
+    "bd_conv_wgrad": (i32, [vp, i64, vp, i64, vp, vp] + [i32] * 10 + [vp]),
     "bd_pack_conv_weight": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "bd_cast_f32_to_f16": (i32, [vp, vp, sz, vp]),
     "bd_colsum_f16": (i32, [vp, i64, vp, i64, i32, i64, i32, i32, vp]),
@@ -76,7 +76,7 @@ _SIGS = {
     "bd_attention_bwd": (i32, [vp, i64, vp, vp, i64, vp, i64, vp, i32, i32, i32, i32, f32, i32, vp]),
     "bd_gradnorm_workspace_floats": (sz, []),
     "bd_grad_norm": (i32, [vp, sz, vp, vp, vp]),
-    "bd_adam_step": (i32, [vp, vp, vp, vp, sz, vp, f32, f32, f32, f32, f32, vp, vp, vp]),
+    "bd_adam_step": (i32, [vp, vp, vp, vp, sz, vp, i32, f32, f32, f32, f32, f32, vp, vp, vp]),
     "bd_scaler_update": (i32, [vp, vp, f32, f32, i32, vp]),
 }
 

@@ -70,8 +70,9 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(
     const float* __restrict__ target, const float* __restrict__ R_explicit, const float* __restrict__ noise,
     const int64_t* __restrict__ t, const float* __restrict__ alphas, const float* __restrict__ acp,
     float* __restrict__ x_noisy, float* __restrict__ eps_target, float* __restrict__ noise_out, int B, int CHW4,
-    uint64_t seed, uint64_t offset) {
+    uint64_t seed, uint64_t offset, const int* __restrict__ noise_counter) {
   const int b = blockIdx.y;
+  if (noise_counter) offset += (uint64_t)(uint32_t)(*noise_counter);  // fresh stream per graph replay
   const int64_t ti = t[b];
   const float al = alphas[ti], ac = acp[ti];
   // loss.py:268-270 and scheduling_ddpm.py:432-438, same op order, each op rounded separately
@@ -341,12 +342,13 @@ __global__ void gradnorm_final_kernel(const float* __restrict__ partial, int np,
 }
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, size_t n,
-                                                   const float* __restrict__ lr_p, float b1, float b2, float eps,
-                                                   float wd, float max_norm, const int* __restrict__ step_p,
-                                                   const float* __restrict__ state) {
+                                                   const float* __restrict__ lr_p, int lr_len, float b1, float b2,
+                                                   float eps, float wd, float max_norm,
+                                                   const int* __restrict__ step_p, const float* __restrict__ state) {
   if (state[2] != 0.0f) return;  // found_inf: skip the step (GradScaler semantics)
-  const float lr = *lr_p;
   const int step = *step_p + 1;
+  // LambdaLR semantics: the k-th optimizer.step() (k = 0, 1, ...) uses lr_table[k]
+  const float lr = lr_p[lr_len > 1 ? min(step - 1, lr_len - 1) : 0];
   // unscale and clip_grad_norm_: coef = min(1, max_norm / (norm + 1e-6))
   float coef = 1.0f / state[0];
   if (max_norm > 0.0f) coef *= fminf(1.0f, max_norm / (state[3] + 1e-6f));
@@ -404,7 +406,7 @@ int bd_device_supported(void) {
 int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigger, const float* target,
                   const float* R_explicit, const float* noise, const int64_t* t, const float* alphas,
                   const float* alphas_cumprod, float* x_noisy, float* eps_target, float* noise_out, int B, int C,
-                  int H, int W, int T, uint64_t seed, uint64_t offset, void* stream) {
+                  int H, int W, int T, uint64_t seed, uint64_t offset, const int* noise_counter, void* stream) {
   BD_CHECK_ARG(img && t && alphas && alphas_cumprod && x_noisy && eps_target, "bd_batch_prep: null pointer");
   BD_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && T > 0, "bd_batch_prep: bad shape");
   BD_CHECK_ARG(((size_t)C * H * W) % 4 == 0, "bd_batch_prep: C*H*W must be a multiple of 4");
@@ -414,7 +416,7 @@ int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigg
   dim3 grid(ceil_div(chw4, 256) < 64 ? ceil_div(chw4, 256) : 64, B);
   batch_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, is_poison, trigger, target, R_explicit, noise, t,
                                                            alphas, alphas_cumprod, x_noisy, eps_target, noise_out, B,
-                                                           chw4, seed, offset);
+                                                           chw4, seed, offset, noise_counter);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
@@ -518,11 +520,11 @@ int bd_grad_norm(const float* grad, size_t n, float* partial, float* state, void
   return BD_OK;
 }
 int bd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* lr,
-                 float beta1, float beta2, float eps, float weight_decay, float max_norm, const int* step,
+                 int lr_len, float beta1, float beta2, float eps, float weight_decay, float max_norm, const int* step,
                  float* state, void* stream) {
   BD_CHECK_ARG(param && grad && exp_avg && exp_avg_sq && lr && step && state && n > 0, "bd_adam_step: bad argument");
-  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2,
-                                                                 eps, weight_decay, max_norm, step, state);
+  adam_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, lr, lr_len, beta1,
+                                                                 beta2, eps, weight_decay, max_norm, step, state);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -269,10 +269,12 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
       int kk = i % TK, mm = i / TK;  // consecutive threads -> consecutive k (fast when sak == 1)
       int m = m0 + mm, k = k0 + kk;
       float v = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f;
-      if (act_silu_a) v = silu_f(v);
+      if (act_silu_a == 1) v = silu_f(v);
       As[kk][mm] = v;
       int nn = i / TK, n = n0 + nn;
-      Bs[kk][nn] = (n < N && k < K) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
+      float bv = (n < N && k < K) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
+      if (act_silu_a == 2) bv = silu_f(bv);
+      Bs[kk][nn] = bv;
     }
     __syncthreads();
 #pragma unroll
@@ -310,17 +312,16 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const int64_t* __restrict
                                                        const float* __restrict__ b2, float* __restrict__ sin_out,
                                                        float* __restrict__ h1, float* __restrict__ emb,
                                                        __half* __restrict__ silu_emb, int dim, int temb, int flip,
-                                                       float freq_shift) {
+                                                       const float* __restrict__ freqs) {
   extern __shared__ float sm[];
   float* se = sm;         // [dim]
   float* sa = sm + dim;   // [temb]
   const int b = blockIdx.x, half_dim = dim / 2;
   const float tv = (float)t[b];
   for (int i = threadIdx.x; i < half_dim; i += blockDim.x) {
-    // embeddings.py:41-52: exponent = -ln(10000) * i / (half - shift); emb = t * exp(exponent)
-    float ex = -9.210340371976184f * (float)i;
-    ex = ex / ((float)half_dim - freq_shift);
-    float arg = tv * expf(ex);
+    // embeddings.py:41-52: emb = t * exp(-ln(10000) * i / (half - shift)); the frequency table is evaluated on the
+    // host with the reference's own torch expression so the sin/cos arguments are bit-identical
+    float arg = __fmul_rn(tv, freqs[i]);
     float sv = sinf(arg), cv = cosf(arg);
     int is = flip ? half_dim + i : i, ic = flip ? i : half_dim + i;
     se[is] = sv;
@@ -431,7 +432,7 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restr
     if (co < Cout) {
 #pragma unroll
       for (int k = 0; k < KMAX; ++k)
-        if (k < K) atomicAdd(dw + (int64_t)co * K + k, acc[k]);
+        if (k < K) atomicAdd(dw + ((int64_t)(k % 9) * Cout + co) * Cin + k / 9, acc[k]);
       if (dbias) atomicAdd(dbias + co, bacc);
     }
   }
@@ -619,10 +620,10 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
 
 int bd_temb_mlp(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* sin_out,
                 float* h1, float* emb, void* silu_emb_f16, int B, int dim, int temb, int flip_sin_to_cos,
-                float freq_shift, void* stream) {
-  BD_CHECK_ARG(t && w1 && b1 && w2 && b2 && emb && B > 0 && dim > 0 && dim % 2 == 0 && temb > 0, "bd_temb_mlp: bad argument");
+                const float* freqs, void* stream) {
+  BD_CHECK_ARG(t && w1 && b1 && w2 && b2 && emb && freqs && B > 0 && dim > 0 && dim % 2 == 0 && temb > 0, "bd_temb_mlp: bad argument");
   temb_mlp_kernel<<<B, 256, (dim + temb) * sizeof(float), (cudaStream_t)stream>>>(
-      t, w1, b1, w2, b2, sin_out, h1, emb, (__half*)silu_emb_f16, dim, temb, flip_sin_to_cos, freq_shift);
+      t, w1, b1, w2, b2, sin_out, h1, emb, (__half*)silu_emb_f16, dim, temb, flip_sin_to_cos, freqs);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -1,0 +1,178 @@
+"""The poisoned DDPM training step of baddiffusion.py:593-615 as one device-resident kernel sequence:
+
+    batch-prep (poison blend + add_noise + loss target, K11) -> UNet forward -> MSE + d(eps_hat) (K12)
+    -> UNet backward -> [NCCL all-reduce of the flat fp32 gradient buffer] -> global-norm -> clip + Adam -> scaler
+
+captured in CUDA graphs (the only host work per step is the H2D copy of the batch and the graph launches).
+Mixed precision follows the reference's fp16 autocast + GradScaler recipe (baddiffusion.py:116,608): fp16 operands,
+fp32 accumulation and master weights, dynamic loss scale with skip-on-overflow.
+
+Multi-GPU: one process per GPU, each rank owns B/world samples, ONE all-reduce (average) over the
+flat gradient buffer per step; clip-by-global-norm and Adam then run identically on every rank.
+"""
+from __future__ import annotations
+
+import math
+import os
+from typing import Optional
+
+import torch
+
+from . import ops
+from .schedulers import DDPMScheduler
+from .unet import UNet2DModel
+
+
+def cosine_lr_lambda(step: int, warmup: int, total: int, num_cycles: float = 0.5) -> float:
+    """D/optimization.py:134-138 (get_cosine_schedule_with_warmup)."""
+    if step < warmup:
+        return float(step) / float(max(1, warmup))
+    progress = float(step - warmup) / float(max(1, total - warmup))
+    return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+
+class Trainer:
+    def __init__(self, model: UNet2DModel, noise_sched: DDPMScheduler, batch: int, trigger: torch.Tensor,
+                 target: torch.Tensor, lr: float = 2e-4, total_steps: int = 23450, warmup_steps: int = 500,
+                 max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, init_scale: float = 65536.0,
+                 growth_interval: int = 2000, use_graph: Optional[bool] = None, process_group=None, seed: int = 0,
+                 lr_table_len: int = 0):
+        if not model.device.type == "cuda":
+            raise RuntimeError("Trainer needs the model on a CUDA device")
+        self.model, self.sched, self.B = model, noise_sched, batch
+        dev = model.device
+        self.dev = dev
+        self.pg = process_group
+        self.world = torch.distributed.get_world_size(process_group) if process_group is not None else 1
+        self.use_graph = (os.environ.get("BD_NO_GRAPH", "0") != "1") if use_graph is None else use_graph
+        cfg = model.config
+        S = cfg.sample_size if isinstance(cfg.sample_size, int) else cfg.sample_size[0]
+        C = cfg.in_channels
+        self.shape = (batch, C, S, S)
+        noise_sched._to_device(dev)
+        self.alphas, self.acp = noise_sched._alphas_dev, noise_sched._acp_dev
+        self.T = noise_sched.config.num_train_timesteps
+        self.trigger = trigger.to(dev, torch.float32).contiguous()
+        self.target = target.to(dev, torch.float32).contiguous()
+        # static device buffers (graph inputs / outputs)
+        self.img = torch.zeros(self.shape, device=dev)
+        self.isp = torch.zeros(batch, dtype=torch.uint8, device=dev)
+        self.t = torch.zeros(batch, dtype=torch.int64, device=dev)
+        self.noise = torch.zeros(self.shape, device=dev)
+        self.x_noisy = torch.empty(self.shape, device=dev)
+        self.eps_target = torch.empty(self.shape, device=dev)
+        self.d_eps = torch.empty(self.shape, device=dev)
+        self.loss = torch.zeros(1, device=dev)
+        self.mse_part = torch.empty(1024, device=dev)
+        self.norm_part = torch.empty(1024, device=dev)
+        # optimizer state on the flat buffers
+        self.eng = model.engine(batch, True)
+        self.flat = model.flat_params
+        self.gflat = model.flat_grads(attach=True)
+        self.m = torch.zeros_like(self.flat)
+        self.v = torch.zeros_like(self.flat)
+        self.state = torch.tensor([init_scale, 0.0, 0.0, 0.0, 0.0], device=dev)  # scale, tracker, found_inf, norm, skipped
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # successful optimizer steps
+        self.iter_dev = torch.zeros(1, dtype=torch.int32, device=dev)   # iterations (Philox stream counter)
+        n_lr = lr_table_len if lr_table_len > 0 else total_steps + 1
+        lrs = [lr * cosine_lr_lambda(i, warmup_steps, total_steps) for i in range(n_lr)]
+        self.lr_table = torch.tensor(lrs, dtype=torch.float32, device=dev)
+        self.max_grad_norm, self.betas, self.eps = max_grad_norm, betas, eps
+        self.growth_interval = growth_interval
+        self.seed = seed
+        self.host_step = 0
+        self._g_fb = None
+        self._g_opt = None
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ the kernel sequence
+    def _fwd_bwd(self, philox_noise: bool):
+        eng = self.eng
+        ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16)
+        ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
+                       noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
+                       x_noisy=self.x_noisy, eps_target=self.eps_target, noise_out=None, noise_counter=self.iter_dev)
+        self.iter_dev.add_(1)
+        eng.io["x"], eng.io["t"], eng.io["d_eps"] = self.x_noisy, self.t, self.d_eps
+        eng.run_forward()
+        ops.mse_fwd_bwd(eng.eps_hat, self.eps_target, self.loss, self.d_eps, self.mse_part, self.state[0:1])
+        self.gflat.zero_()
+        eng.run_backward()
+
+    def _optimizer(self):
+        ops.grad_norm(self.gflat, self.norm_part, self.state)
+        ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr_table, self.step_dev, self.state,
+                      beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, max_norm=self.max_grad_norm,
+                      lr_len=self.lr_table.numel())
+        ops.scaler_update(self.state, self.step_dev, 2.0, 0.5, self.growth_interval)
+
+    def _capture(self, fn):
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            fn()  # warm-up outside capture (function attributes, lazy init)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn()
+        return g
+
+    def _ensure_graphs(self, philox_noise: bool):
+        if not self.use_graph or self._g_fb is not None:
+            return
+        # the warm-up run must not disturb training state: snapshot what the optimizer mutates
+        snap = (self.flat.clone(), self.m.clone(), self.v.clone(), self.state.clone(), self.step_dev.clone(),
+                self.iter_dev.clone())
+        before = ops.launch_count()
+        self._g_fb = self._capture(lambda: self._fwd_bwd(philox_noise))
+        self._g_opt = self._capture(self._optimizer)
+        self.launches_per_step = (ops.launch_count() - before) // 2 + 1  # + the memset of the gradient buffer
+        for dst, src in zip((self.flat, self.m, self.v, self.state, self.step_dev, self.iter_dev), snap):
+            dst.copy_(src)
+        self._philox = philox_noise
+
+    # ------------------------------------------------------------------ public API
+    def load_batch(self, image: torch.Tensor, is_poison: torch.Tensor, noise: Optional[torch.Tensor] = None,
+                   t: Optional[torch.Tensor] = None):
+        """Host (pinned) or device tensors -> the static device buffers.  `t` / `noise` default to the reference's
+        draws: t = randint on the device (baddiffusion.py:600); noise in-kernel (Philox) unless given."""
+        self.img.copy_(image, non_blocking=True)
+        self.isp.copy_(is_poison.to(torch.uint8), non_blocking=True)
+        if t is None:
+            self.t.copy_(torch.randint(0, self.T, (self.B,), device=self.dev))
+        else:
+            self.t.copy_(t, non_blocking=True)
+        if noise is not None:
+            self.noise.copy_(noise, non_blocking=True)
+
+    def step(self, image: torch.Tensor, is_poison: torch.Tensor, noise: Optional[torch.Tensor] = None,
+             t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """One optimisation step on one (local) batch; returns the device loss tensor (no host sync)."""
+        self.load_batch(image, is_poison, noise, t)
+        return self.step_resident(philox_noise=noise is None)
+
+    def step_resident(self, philox_noise: bool = True) -> torch.Tensor:
+        """Same, with the batch already in the static device buffers (img / isp / t / noise)."""
+        if self.use_graph:
+            self._ensure_graphs(philox_noise)
+            assert self._philox == philox_noise, "noise mode is baked into the captured graph"
+            self._g_fb.replay()
+        else:
+            self._fwd_bwd(philox_noise)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+        if self.use_graph:
+            self._g_opt.replay()
+        else:
+            self._optimizer()
+        self.host_step += 1
+        self.model.mark_params_changed()
+        return self.loss
+
+    @property
+    def loss_scale(self) -> float:
+        return float(self.state[0])
+
+    @property
+    def grad_norm(self) -> float:
+        return float(self.state[3])

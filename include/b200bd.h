@@ -55,7 +55,9 @@ uint64_t bd_launch_count(void);
 int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigger, const float* target,
                   const float* R_explicit, const float* noise, const int64_t* t, const float* alphas,
                   const float* alphas_cumprod, float* x_noisy, float* eps_target, float* noise_out, int B, int C,
-                  int H, int W, int T, uint64_t seed, uint64_t offset, void* stream);
+                  int H, int W, int T, uint64_t seed, uint64_t offset,
+                  const int* noise_counter /* device int added to `offset` (nullable): new noise per graph replay */,
+                  void* stream);
 
 /* K12  loss.py:301 F.mse_loss(target, eps_hat) and its gradient 2(eps_hat-target)/n * loss_scale.
  *   partial: workspace of >= bd_mse_workspace_floats() floats; loss: 1 float; grad nullable (f32, same
@@ -90,13 +92,14 @@ int bd_finalize_images(const float* x, float* nhwc01, uint8_t* nhwc_u8, int B, i
  * ---------------------------------------------------------------------------------------------- */
 int bd_temb_mlp(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* sin_out,
                 float* h1, float* emb, void* silu_emb_f16, int B, int dim, int temb, int flip_sin_to_cos,
-                float freq_shift, void* stream);
+                const float* freqs /* (dim/2) f32: exp(-ln(1e4) * i / (dim/2 - freq_shift)), host-evaluated */,
+                void* stream);
 
 /* generic small fp32 GEMM (strided, optionally batched): C[m,n] (+)= sum_k A[m,k]*B[k,n] (+ bias[n]).
  * Used for the tiny linears of the timestep path and their gradients (exact fp32, SIMT).              */
 int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t sbk, int64_t sbn, float* C,
-             int64_t scm, int64_t scn, const float* bias, int M, int N, int K, int accumulate, int act_silu_a,
-             void* stream);
+             int64_t scm, int64_t scn, const float* bias, int M, int N, int K, int accumulate,
+             int act /* 0 none, 1 silu(A), 2 silu(B) */, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K4/K5  torch.nn.GroupNorm (+SiLU) on fp16 NHWC views; statistics in fp32 (two-stage, fixed order).
@@ -204,7 +207,8 @@ size_t bd_attention_bwd_workspace_bytes(int B, int S, int C, int heads);
  * ---------------------------------------------------------------------------------------------- */
 size_t bd_gradnorm_workspace_floats(void);
 int bd_grad_norm(const float* grad, size_t n, float* partial, float* state, void* stream);
-int bd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n, const float* lr,
+int bd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, size_t n,
+                 const float* lr /* device table of lr_len entries, indexed by *step (cosine schedule) */, int lr_len,
                  float beta1, float beta2, float eps, float weight_decay, float max_norm, const int* step,
                  float* state, void* stream);
 int bd_scaler_update(float* state, int* step, float growth, float backoff, int growth_interval, void* stream);
