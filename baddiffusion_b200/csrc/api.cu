@@ -27,6 +27,11 @@ struct FpropCall {
   int N, ks; bool b_mn; bool batched; bool flip_taps;
   const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias; int HW_rowbias;
   const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+  int a_stride;
+  int a_H, a_W;
+  int ntap_override;
+  int tap_dx[9], tap_dy[9], tap_z[9];
+  int64_t out_sn, out_sh, out_sw, out_off;
 };
 struct WgradCall {
   const void* a; int64_t ld_a; int Mtot;
@@ -34,6 +39,7 @@ struct WgradCall {
   int NB, H, W, ks; bool batched;
   void* y; int64_t ld_y; int out_mode;
   int zcount;
+  int b_stride, b_pad, b_H, b_W;
 };
 int fprop_supported(const FpropCall& c);
 int fprop_launch(const FpropCall& c, cudaStream_t st);
@@ -139,7 +145,17 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
   c.bias = a->bias; c.bias2 = a->bias2; c.rowbias = a->rowbias; c.ld_rowbias = a->ld_rowbias; c.HW_rowbias = a->H * a->W;
   c.residual = a->residual; c.ld_res = a->ld_res; c.scale = a->out_scale; c.y = a->y; c.ld_y = a->ld_y;
   c.out_f32 = a->out_dtype == BD_OUT_F32;
-  const bool can = a->mode == BD_CONV_S1 && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
+  if (a->mode == BD_CONV_S2_PAD01) {
+    // Downsample2D: the A tile is sampled at every other pixel by the TMA unit (elementStrides = 2); tiles run over
+    // the OUTPUT grid.  tap (r, s) reads input (2*ho + r - pad, 2*wo + s - pad); out-of-bounds -> zero fill.
+    int Ho, Wo;
+    conv_out_hw(a, &Ho, &Wo);
+    c.a_stride = 2; c.a_H = a->H; c.a_W = a->W; c.H = Ho; c.W = Wo; c.HW_rowbias = Ho * Wo;
+    c.ntap_override = 9;
+    for (int t = 0; t < 9; ++t) { c.tap_dy[t] = t / 3 - a->pad; c.tap_dx[t] = t % 3 - a->pad; c.tap_z[t] = t; }
+  }
+  const bool s2ok = a->mode == BD_CONV_S1 || (a->H % 2 == 0 && a->W % 2 == 0 && !a->x2);
+  const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
   if (a->impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
     set_error("bd_conv_fwd: tcgen05 path requested but shape unsupported (Cin=%d Cout=%d H=%d W=%d mode=%d)", a->Cin, a->Cout, a->H, a->W, a->mode);
     return BD_ERR_UNSUPPORTED;
@@ -169,14 +185,38 @@ int bd_conv_dgrad(const bd_conv_args* a, void* stream) {
   c.N = a->Cin; c.ks = a->ksize; c.b_mn = true; c.batched = false; c.flip_taps = true;
   c.bias = nullptr; c.residual = a->residual; c.ld_res = a->ld_res; c.scale = a->out_scale; c.y = a->y; c.ld_y = a->ld_y;
   c.out_f32 = a->out_dtype == BD_OUT_F32;
-  const bool can = a->mode == BD_CONV_S1 && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
+  const bool s2 = a->mode == BD_CONV_S2_PAD01;
+  if (s2) { c.H = Ho; c.W = Wo; }  // tiles run over the dY grid; each launch fills one parity class of dX
+  const bool s2ok = !s2 || (a->H == 2 * Ho && a->W == 2 * Wo);
+  const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
   if (a->impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
     set_error("bd_conv_dgrad: tcgen05 path requested but shape unsupported");
     return BD_ERR_UNSUPPORTED;
   }
   if (a->impl == BD_IMPL_UMMA || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
-    rc = umma::fprop_launch(c, st);
-    if (rc) return rc;
+    if (!s2) {
+      rc = umma::fprop_launch(c, st);
+      if (rc) return rc;
+    } else {
+      // dX[2i+ah, 2j+aw] = sum over taps (r, s) with (ah + pad - r), (aw + pad - s) even of
+      //                    dY[i + (ah + pad - r)/2, j + (aw + pad - s)/2] W[r, s]^T
+      for (int ah = 0; ah < 2; ++ah)
+        for (int aw = 0; aw < 2; ++aw) {
+          umma::FpropCall q = c;
+          q.ntap_override = 0;
+          for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+              const int nh = ah + a->pad - r, nw = aw + a->pad - s;
+              if ((nh & 1) || (nw & 1)) continue;
+              const int t = q.ntap_override++;
+              q.tap_dy[t] = nh / 2; q.tap_dx[t] = nw / 2; q.tap_z[t] = r * 3 + s;
+            }
+          q.out_sn = (int64_t)a->H * a->W; q.out_sh = 2 * (int64_t)a->W; q.out_sw = 2;
+          q.out_off = (int64_t)ah * a->W + aw;
+          rc = umma::fprop_launch(q, st);
+          if (rc) return rc;
+        }
+    }
   } else {
     simt_conv_launch(a, true, st);
   }
@@ -197,7 +237,16 @@ int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, fl
   c.b = x; c.ld_b = ld_x; c.Ntot = Cin;
   c.NB = B; c.H = H; c.W = W; c.ks = ksize; c.batched = false;
   c.y = dw; c.ld_y = Cin; c.out_mode = 0; c.zcount = ksize * ksize;
-  const bool can = mode == BD_CONV_S1 && umma::wgrad_supported(c);
+  int64_t npix = (int64_t)B * H * W;
+  bool s2ok = true;
+  if (mode == BD_CONV_S2_PAD01) {
+    // k-blocks run over the dY grid; X is sampled with stride 2 by the TMA unit
+    const int Ho = (H + (pad ? 2 : 1) - 3) / 2 + 1, Wo = (W + (pad ? 2 : 1) - 3) / 2 + 1;
+    s2ok = ksize == 3 && H == 2 * Ho && W == 2 * Wo;
+    c.b_stride = 2; c.b_pad = pad; c.b_H = H; c.b_W = W; c.H = Ho; c.W = Wo;
+    npix = (int64_t)B * Ho * Wo;
+  }
+  const bool can = s2ok && umma::wgrad_supported(c);
   if (impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
     set_error("bd_conv_wgrad: tcgen05 path requested but shape unsupported");
     return BD_ERR_UNSUPPORTED;
@@ -211,7 +260,7 @@ int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, fl
     int rc = umma::wgrad_launch(c, st);
     if (rc) return rc;
     if (dbias) {
-      rc = bd_colsum_f16(dy, ld_dy, dbias, 0, 1, (int64_t)B * H * W, Cout, accumulate, stream);
+      rc = bd_colsum_f16(dy, ld_dy, dbias, 0, 1, npix, Cout, accumulate, stream);
       if (rc) return rc;
     }
   } else {

@@ -38,7 +38,7 @@ __host__ __device__ static inline int ceil_div(long long a, long long b) { retur
 
 int num_sms();  // cached cudaDevAttrMultiProcessorCount of the current device
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 __device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1,22 +1,24 @@
 // GroupNorm (+SiLU) forward / backward on fp16 NHWC views with fp32/fp64 statistics (K4/K5).
-// HBM-bound: forward reads x twice (second read is L2-resident at the UNet's sizes) and writes y once.
+// HBM-bound: forward reads x twice (the second read is L2-resident at the UNet's sizes) and writes y once.
 // Reductions are two-stage with a fixed summation order => bitwise reproducible run to run.
+// Thread mapping (all kernels): block = C8 * rows threads, C8 = C/8; a thread owns ONE 8-channel vector
+// (v = tid % C8) for its whole life, so per-channel parameters live in registers and every warp reads
+// consecutive 16-byte vectors of a pixel row (coalesced); pixels are strided by `rows` with 4 loads in flight.
 #include "common.cuh"
 
 namespace bd {
-void count_launch(int n);
 
 constexpr int kGnMaxSplits = 32;
+constexpr int UNR = 4;
 
-static inline int gn_splits(int B, int HW) {
-  int want = ceil_div(2 * num_sms(), B > 0 ? B : 1);
-  int cap = HW / 64 > 0 ? HW / 64 : 1;  // >= 64 pixels per block
+static inline int gn_splits(int B, int HW, int rows) {
+  int want = ceil_div(4 * num_sms(), B > 0 ? B : 1);
+  int cap = HW / (rows * UNR) > 0 ? HW / (rows * UNR) : 1;
   int s = want < cap ? want : cap;
   if (s > kGnMaxSplits) s = kGnMaxSplits;
   return s < 1 ? 1 : s;
 }
 
-// block = C8 * rows threads (rows = max(1, 256 / C8)); thread owns channel-vector v = tid % C8
 // smem: red[rows][C][2]
 __global__ void gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float* __restrict__ work, int HW, int C,
                                 int G, int splits) {
@@ -25,12 +27,21 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int p0 = (int)((int64_t)HW * sp / splits), p1 = (int)((int64_t)HW * (sp + 1) / splits);
-  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0}, f[8];
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
-  for (int p = p0 + r; p < p1; p += rows) {
-    unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), f);
+  for (int p = p0 + r; p < p1; p += rows * UNR) {
+    half8 hv[UNR];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) hv[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) {
+        float f[8];
+        unpack8(hv[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { s[k] += f[k]; q[k] += f[k] * f[k]; }
+      }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -70,16 +81,16 @@ __device__ __forceinline__ void gn_finalize_stats(const float* __restrict__ work
   }
 }
 
-__global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx,
-                                                       __half* __restrict__ y, int64_t ldy,
-                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
-                                                       const float* __restrict__ work, float* __restrict__ stats,
-                                                       int HW, int C, int G, int splits, int asplits, float eps,
-                                                       int apply_silu) {
+// block = C8 * rows threads; smem: mean[G], rstd[G]
+__global__ void gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
+                                const float* __restrict__ gamma, const float* __restrict__ beta,
+                                const float* __restrict__ work, float* __restrict__ stats, int HW, int C, int G,
+                                int splits, int asplits, float eps, int apply_silu) {
   extern __shared__ float sm[];
   float* sm_mean = sm;
   float* sm_rstd = sm + G;
-  const int b = blockIdx.y, cpg = C / G, C8 = C / 8;
+  const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
+  const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   gn_finalize_stats(work, sm_mean, sm_rstd, b, G, splits, HW, cpg, eps);
   __syncthreads();
   if (blockIdx.x == 0 && stats)
@@ -87,95 +98,121 @@ __global__ void __launch_bounds__(256) gn_apply_kernel(const __half* __restrict_
       stats[((int64_t)b * G + g) * 2 + 0] = sm_mean[g];
       stats[((int64_t)b * G + g) * 2 + 1] = sm_rstd[g];
     }
-  const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
-  const int64_t total = (int64_t)(p1 - p0) * C8;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int v = (int)(i % C8);
-    const int64_t p = p0 + i / C8;
-    float f[8];
-    unpack8(*reinterpret_cast<const half8*>(x + ((int64_t)b * HW + p) * ldx + v * 8), f);
-    const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
-    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-    const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  // y = x * a + c  with a = rstd*gamma, c = beta - mean*rstd*gamma (per channel, in registers)
+  float a[8], c[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int g = (v * 8 + k) / cpg;
-      float z = (f[k] - sm_mean[g]) * sm_rstd[g] * gm[k] + bt[k];
-      f[k] = apply_silu ? silu_f(z) : z;
-    }
-    *reinterpret_cast<half8*>(y + ((int64_t)b * HW + p) * ldy + v * 8) = pack8(f);
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k, g = ch / cpg;
+    a[k] = sm_rstd[g] * gamma[ch];
+    c[k] = beta[ch] - sm_mean[g] * a[k];
+  }
+  const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
+  const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
+  __half* yb = y + (int64_t)b * HW * ldy + v * 8;
+  for (int p = p0 + r; p < p1; p += rows * UNR) {
+    half8 hv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) hv[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) {
+        float f[8];
+        unpack8(hv[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float z = fmaf(f[k], a[k], c[k]);
+          f[k] = apply_silu ? silu_f(z) : z;
+        }
+        *reinterpret_cast<half8*>(yb + (int64_t)(p + u * rows) * ldy) = pack8(f);
+      }
   }
 }
 
-// ---------------------------------------------------------------------------------------------
-// backward pass 1: per (b, split, c): s1 = sum dz, s2 = sum dz * xhat    (dz = dy * silu'(z))
-// block = C8 * rows threads, smem red[rows][C][2] + mean/rstd [2G]
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float dsilu(float z) {
-  float sg = sigmoid_f(z);
+  float sg = __fdividef(1.0f, 1.0f + __expf(-z));
   return sg * (1.0f + z * (1.0f - sg));
 }
 
-__global__ void gn_bwd_reduce_kernel(const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy,
-                                     int64_t lddy, const float* __restrict__ gamma, const float* __restrict__ beta,
-                                     const float* __restrict__ stats, float* __restrict__ work, int HW, int C, int G,
-                                     int splits, int apply_silu) {
+// backward pass 1: per (b, split, c): s1 = sum dz, s2 = sum dz * xhat    (dz = dy * silu'(z))
+// In the loop only  z = x*a + c  (a = rstd*gamma, c = beta - mean*a) is formed; sum dz*xhat is recovered from
+// sum dz*x afterwards, so the per-thread state is 4 x 8 registers.
+__global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
+    const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    float* __restrict__ work, int HW, int C, int G, int splits, int apply_silu) {
   extern __shared__ float red[];
   const int C8 = C / 8, rows = blockDim.x / C8, cpg = C / G;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const int b = blockIdx.y, sp = blockIdx.x;
   const int p0 = (int)((int64_t)HW * sp / splits), p1 = (int)((int64_t)HW * (sp + 1) / splits);
-  float mean[8], rstd[8], gm[8], bt[8];
+  float a[8], c[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    const int c = v * 8 + k, g = c / cpg;
-    mean[k] = stats[((int64_t)b * G + g) * 2 + 0];
-    rstd[k] = stats[((int64_t)b * G + g) * 2 + 1];
-    gm[k] = gamma[c];
-    bt[k] = beta[c];
+    const int ch = v * 8 + k, g = ch / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    a[k] = rstd * gamma[ch];
+    c[k] = beta[ch] - mean * a[k];
   }
-  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0}, fx[8], fd[8];
-  for (int p = p0 + r; p < p1; p += rows) {
-    unpack8(*reinterpret_cast<const half8*>(x + ((int64_t)b * HW + p) * ldx + v * 8), fx);
-    unpack8(*reinterpret_cast<const half8*>(dy + ((int64_t)b * HW + p) * lddy + v * 8), fd);
+  float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
+  const __half* db = dy + (int64_t)b * HW * lddy + v * 8;
+  for (int p = p0 + r; p < p1; p += rows * 2) {
+    const bool two = p + rows < p1;
+    half8 hx0 = *reinterpret_cast<const half8*>(xb + (int64_t)p * ldx);
+    half8 hd0 = *reinterpret_cast<const half8*>(db + (int64_t)p * lddy);
+    half8 hx1 = hx0, hd1 = hd0;
+    if (two) {
+      hx1 = *reinterpret_cast<const half8*>(xb + (int64_t)(p + rows) * ldx);
+      hd1 = *reinterpret_cast<const half8*>(db + (int64_t)(p + rows) * lddy);
+    }
+    float fx[8], fd[8];
+    unpack8(hx0, fx);
+    unpack8(hd0, fd);
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-      float xh = (fx[k] - mean[k]) * rstd[k];
       float dz = fd[k];
-      if (apply_silu) dz *= dsilu(xh * gm[k] + bt[k]);
+      if (apply_silu) dz *= dsilu(fmaf(fx[k], a[k], c[k]));
       s1[k] += dz;
-      s2[k] += dz * xh;
+      s2[k] = fmaf(dz, fx[k], s2[k]);
+    }
+    if (two) {
+      unpack8(hx1, fx);
+      unpack8(hd1, fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz = fd[k];
+        if (apply_silu) dz *= dsilu(fmaf(fx[k], a[k], c[k]));
+        s1[k] += dz;
+        s2[k] = fmaf(dz, fx[k], s2[k]);
+      }
     }
   }
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
-    red[(r * C + v * 8 + k) * 2 + 0] = s1[k];
-    red[(r * C + v * 8 + k) * 2 + 1] = s2[k];
+    // sum dz*xhat = rstd * (sum dz*x - mean * sum dz)
+    const int ch = v * 8 + k, g = ch / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    red[(r * C + ch) * 2 + 0] = s1[k];
+    red[(r * C + ch) * 2 + 1] = rstd * (s2[k] - mean * s1[k]);
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float a = 0.f, q = 0.f;
+  for (int ch = threadIdx.x; ch < C; ch += blockDim.x) {
+    float sa = 0.f, sq = 0.f;
     for (int rr = 0; rr < rows; ++rr) {
-      a += red[(rr * C + c) * 2 + 0];
-      q += red[(rr * C + c) * 2 + 1];
+      sa += red[(rr * C + ch) * 2 + 0];
+      sq += red[(rr * C + ch) * 2 + 1];
     }
     float* w = work + (((int64_t)b * splits + sp) * 2) * C;
-    w[c] = a;
-    w[C + c] = q;
+    w[ch] = sa;
+    w[C + ch] = sq;
   }
 }
 
-// backward pass 2: dx = rstd * (dz*gamma - A/n - xhat * Bq/n) (+ add_dx)
-__global__ void __launch_bounds__(256) gn_bwd_apply_kernel(
-    const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
-    const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
-    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-    const float* __restrict__ work, int HW, int C, int G, int splits, int asplits, int apply_silu) {
-  extern __shared__ float sm[];
-  float* gA = sm;       // [G] sum_c gamma*s1 / n
-  float* gB = sm + G;   // [G] sum_c gamma*s2 / n
-  const int b = blockIdx.y, cpg = C / G, C8 = C / 8;
+// per (b, g): gA = sum_c gamma*s1 / n, gB = sum_c gamma*s2 / n  -> gab (B, G, 2); one block per sample
+__global__ void gn_bwd_group_kernel(const float* __restrict__ work, const float* __restrict__ gamma,
+                                    float* __restrict__ gab, int HW, int C, int G, int splits) {
+  const int b = blockIdx.x, cpg = C / G;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
@@ -188,49 +225,79 @@ __global__ void __launch_bounds__(256) gn_bwd_apply_kernel(
       a += (double)gamma[c] * s1;
       q += (double)gamma[c] * s2;
     }
-    double n = (double)HW * cpg;
-    gA[g] = (float)(a / n);
-    gB[g] = (float)(q / n);
-  }
-  __syncthreads();
-  const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
-  const int64_t total = (int64_t)(p1 - p0) * C8;
-  for (int64_t i = threadIdx.x; i < total; i += blockDim.x) {
-    const int v = (int)(i % C8);
-    const int64_t p = p0 + i / C8;
-    const int64_t row = (int64_t)b * HW + p;
-    float fx[8], fd[8], fa[8];
-    unpack8(*reinterpret_cast<const half8*>(x + row * ldx + v * 8), fx);
-    unpack8(*reinterpret_cast<const half8*>(dy + row * lddy + v * 8), fd);
-    if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = v * 8 + k, g = c / cpg;
-      const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
-      const float gm = gamma[c];
-      float xh = (fx[k] - mean) * rstd;
-      float dz = fd[k];
-      if (apply_silu) dz *= dsilu(xh * gm + beta[c]);
-      float r = rstd * (dz * gm - gA[g] - xh * gB[g]);
-      if (add) r += fa[k];
-      fx[k] = r;
-    }
-    *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+    const double n = (double)HW * cpg;
+    gab[((int64_t)b * G + g) * 2 + 0] = (float)(a / n);
+    gab[((int64_t)b * G + g) * 2 + 1] = (float)(q / n);
   }
 }
 
-// dgamma[c] (+)= sum_{b,split} s2 ; dbeta[c] (+)= sum s1   (fixed order)
-__global__ void gn_bwd_params_kernel(const float* __restrict__ work, float* __restrict__ dgamma,
-                                     float* __restrict__ dbeta, int BS, int C, int accumulate) {
-  int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s1 = 0.0, s2 = 0.0;
-  for (int i = 0; i < BS; ++i) {
-    s1 += (double)work[(int64_t)i * 2 * C + c];
-    s2 += (double)work[(int64_t)i * 2 * C + C + c];
+// backward pass 2:  dx = rstd*(dz*gamma - gA - xhat*gB) (+ add)  ==  k1*dz + c1*x + c0 (+ add)  with per-channel
+// k1 = rstd*gamma, c1 = -rstd^2*gB, c0 = rstd*(mean*rstd*gB - gA);  z = x*k1 + cz for the SiLU derivative.
+__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
+    const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
+    const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    const float* __restrict__ gab, int HW, int C, int G, int asplits, int apply_silu) {
+  const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
+  const int v = threadIdx.x % C8, r = threadIdx.x / C8;
+  float k1[8], cz[8], c1[8], c0[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k, g = ch / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    const float gA = gab[((int64_t)b * G + g) * 2 + 0], gB = gab[((int64_t)b * G + g) * 2 + 1];
+    k1[k] = rstd * gamma[ch];
+    cz[k] = beta[ch] - mean * k1[k];
+    c1[k] = -rstd * rstd * gB;
+    c0[k] = rstd * (mean * rstd * gB - gA);
   }
-  dgamma[c] = (accumulate ? dgamma[c] : 0.f) + (float)s2;
-  dbeta[c] = (accumulate ? dbeta[c] : 0.f) + (float)s1;
+  const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
+  const int64_t rb = (int64_t)b * HW;
+  for (int p = p0 + r; p < p1; p += rows * 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int pp = p + u * rows;
+      if (pp >= p1) break;
+      const int64_t row = rb + pp;
+      float fx[8], fd[8], fa[8];
+      unpack8(*reinterpret_cast<const half8*>(x + row * ldx + v * 8), fx);
+      unpack8(*reinterpret_cast<const half8*>(dy + row * lddy + v * 8), fd);
+      if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz = fd[k];
+        if (apply_silu) dz *= dsilu(fmaf(fx[k], k1[k], cz[k]));
+        float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
+        if (add) o += fa[k];
+        fx[k] = o;
+      }
+      *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+    }
+  }
+}
+
+// dgamma[c] (+)= sum_{b,split} s2 ; dbeta[c] (+)= sum s1.  block (32 channels x 8 row lanes), fixed order.
+__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ work, float* __restrict__ dgamma,
+                                                            float* __restrict__ dbeta, int BS, int C, int accumulate) {
+  __shared__ float r1[8][33], r2[8][33];
+  const int cl = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + cl;
+  float s1 = 0.f, s2 = 0.f;
+  if (c < C)
+    for (int i = lane_r; i < BS; i += 8) {
+      s1 += work[(int64_t)i * 2 * C + c];
+      s2 += work[(int64_t)i * 2 * C + C + c];
+    }
+  r1[lane_r][cl] = s1;
+  r2[lane_r][cl] = s2;
+  __syncthreads();
+  if (lane_r == 0 && c < C) {
+    float a = 0.f, q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { a += r1[i][cl]; q += r2[i][cl]; }
+    dgamma[c] = (accumulate ? dgamma[c] : 0.f) + q;
+    dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
+  }
 }
 
 }  // namespace bd
@@ -241,7 +308,19 @@ extern "C" {
 
 size_t bd_gn_workspace_floats(int B, int C) {
   // forward needs B*splits*G*2 (G <= C), backward B*splits*2*C
-  return (size_t)(B > 0 ? B : 1) * kGnMaxSplits * 2 * (size_t)C;
+  return (size_t)(B > 0 ? B : 1) * (kGnMaxSplits * 2 * (size_t)C + 2 * (size_t)C);
+}
+
+static inline void gn_geometry(int B, int HW, int C, int* threads, int* rows, int* splits, int* asplits) {
+  const int C8 = C / 8;
+  *rows = C8 >= 256 ? 1 : 256 / C8;
+  *threads = C8 * (*rows);
+  *splits = gn_splits(B, HW, *rows);
+  // the apply passes have no reduction: give them ~8 blocks per SM
+  int want = ceil_div(8 * num_sms(), B);
+  int cap = HW / (*rows) > 0 ? HW / (*rows) : 1;
+  *asplits = want < cap ? want : cap;
+  if (*asplits < 1) *asplits = 1;
 }
 
 int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
@@ -250,12 +329,12 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && C <= 2048,
                "bd_groupnorm_fwd: need C %% 8 == 0, C %% G == 0, ld %% 8 == 0, C <= 2048 (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
-  const int C8 = C / 8, rows = C8 >= 256 ? 1 : 256 / C8, threads = C8 * rows;
-  const int splits = gn_splits(B, HW);
+  int threads, rows, splits, asplits;
+  gn_geometry(B, HW, C, &threads, &rows, &splits, &asplits);
   gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, work, HW, C, G, splits);
-  gn_apply_kernel<<<dim3(splits, B), 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, work, stats, HW, C, G, splits, splits, eps, apply_silu);
+  gn_apply_kernel<<<dim3(asplits, B), threads, 2 * G * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, work, stats, HW, C, G, splits, asplits, eps, apply_silu);
   count_launch(2);
   BD_CHECK_LAUNCH();
   return BD_OK;
@@ -269,15 +348,18 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
                    (!add_dx || ld_add % 8 == 0),
                "bd_groupnorm_bwd: bad shape (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
-  const int C8 = C / 8, rows = C8 >= 256 ? 1 : 256 / C8, threads = C8 * rows;
-  const int splits = gn_splits(B, HW);
+  int threads, rows, splits, asplits;
+  gn_geometry(B, HW, C, &threads, &rows, &splits, &asplits);
   gn_bwd_reduce_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu);
-  gn_bwd_apply_kernel<<<dim3(splits, B), 256, 2 * G * sizeof(float), (cudaStream_t)stream>>>(
+  // group sums live right behind the per-split partials in the workspace
+  float* gab = work + (size_t)B * splits * 2 * C;
+  gn_bwd_group_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(work, gamma, gab, HW, C, G, splits);
+  gn_bwd_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
-      stats, work, HW, C, G, splits, splits, apply_silu);
-  gn_bwd_params_kernel<<<ceil_div(C, 128), 128, 0, (cudaStream_t)stream>>>(work, dgamma, dbeta, B * splits, C, 1);
-  count_launch(3);
+      stats, gab, HW, C, G, asplits, apply_silu);
+  gn_bwd_params_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(work, dgamma, dbeta, B * splits, C, 1);
+  count_launch(4);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }

@@ -43,6 +43,8 @@ struct FpropParams {
   int HW;                // rows per sample for rowbias
   int N;                 // output columns
   int batched;           // B map z += image index (attention)
+  int a_stride;          // A tile origin = tile origin * a_stride + shift (2 for the stride-2 Downsample2D conv)
+  int64_t out_sn, out_sh, out_sw, out_off;  // output pixel index = n*out_sn + h*out_sh + w*out_sw + out_off
   // UMMA smem descriptor fields (16-byte units), host-provided so they can be overridden for bring-up
   uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
   uint32_t idesc;
@@ -58,13 +60,14 @@ struct FpropParams {
   int64_t ld_y;
   int out_f32;
   int* error_flag;
+  int dbg_shift, dbg_boff;  // bring-up experiment: A tile loaded dbg_shift rows early, descriptor start moved back
 };
 
 struct WgradParams {
   int pbw, pbh, pbn;        // pixel box of one k-block (product 64)
   int ptiles_w, ptiles_h;   // k-blocks per image along W / H
   int kblocks_total;        // all k-blocks (NB/pbn * ptiles_h * ptiles_w), or per image when batched
-  int dx, dy_base;          // unused placeholders
+  int b_stride, b_pad;      // B (= X) tile origin = k-block origin * b_stride + tap - b_pad
   int ks;                   // filter size (z = tap -> shift)
   int n_tiles;              // tiles along N
   int batched;              // z = image index (attention dK / dV)
@@ -236,7 +239,7 @@ __global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constan
           uint8_t* sa = smem + stage * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
           mbar_expect_tx(&full[stage], L::kStageBytes);
-          tma_load_4d(mapA, &full[stage], sa, sg.a_c0 + kb * BK, w0 + sg.dx, h0 + sg.dy, n0);
+          tma_load_4d(mapA, &full[stage], sa, sg.a_c0 + kb * BK, w0 * p.a_stride + sg.dx - p.dbg_shift, h0 * p.a_stride + sg.dy, n0);
           const int bz = sg.b_z + (p.batched ? n0 : 0);
           if (!B_MN) {
             tma_load_3d(mapB, &full[stage], sb, sg.b_k0 + kb * BK, n_tile * BN, bz);
@@ -264,7 +267,7 @@ __global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constan
 #pragma unroll
         for (int k = 0; k < BK / 16; ++k) {
           // K-major: advance 16 elements = 32 B inside the 128B swizzle row; MN-major: 16 k-rows = 2048 B
-          const uint64_t ad = make_desc(sa + k * 32, p.a_lbo, p.a_sbo);
+          const uint64_t ad = make_desc(sa + k * 32 + p.dbg_shift * 128, p.a_lbo, p.a_sbo) | ((uint64_t)(p.dbg_boff & 7) << 49);
           const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
           umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
@@ -280,11 +283,12 @@ __global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constan
     const int dn = r / (p.bw * p.bh), dh = (r / p.bw) % p.bh, dw = r % p.bw;
     const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
     const bool valid = n < p.NB && h < p.H && w < p.W;
-    const int64_t m = ((int64_t)n * p.H + h) * p.W + w;
+    const int64_t mlin = ((int64_t)n * p.H + h) * p.W + w;                        // dense pixel index (rowbias)
+    const int64_t m = (int64_t)n * p.out_sn + h * p.out_sh + w * p.out_sw + p.out_off;  // output / residual pixel
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
     tc_fence_after();
     if (ok) {
-      const float* rb = (p.rowbias && valid) ? p.rowbias + (m / p.HW) * p.ld_rowbias : nullptr;
+      const float* rb = (p.rowbias && valid) ? p.rowbias + (mlin / p.HW) * p.ld_rowbias : nullptr;
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
@@ -369,7 +373,7 @@ __global__ void __launch_bounds__(192, 1) umma_wgrad_kernel(const __grid_constan
   const int m_tile = blockIdx.x / p.n_tiles, n_tile = blockIdx.x % p.n_tiles;
   const int z = blockIdx.y;
   int dx = 0, dy = 0;
-  if (!p.batched && p.ks == 3) { dy = z / 3 - 1; dx = z % 3 - 1; }
+  if (!p.batched && p.ks == 3) { dy = z / 3 - p.b_pad; dx = z % 3 - p.b_pad; }
   const int per = (p.kblocks_total + p.splits - 1) / p.splits;
   const int kb_begin = blockIdx.z * per;
   const int kb_end = min(p.kblocks_total, kb_begin + per);
@@ -409,7 +413,7 @@ __global__ void __launch_bounds__(192, 1) umma_wgrad_kernel(const __grid_constan
             tma_load_4d(&tmA, &full[stage], sa + i * (64 * BK * 2), m_tile * BM + i * 64, pw, ph, pn);
 #pragma unroll
           for (int i = 0; i < BN / 64; ++i)
-            tma_load_4d(&tmB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, pw + dx, ph + dy, pn);
+            tma_load_4d(&tmB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, pw * p.b_stride + dx, ph * p.b_stride + dy, pn);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -500,12 +504,12 @@ static PFN_encodeTiled get_encode() {
 
 // rank-4 fp16 map: dims {d0,d1,d2,d3} (d0 contiguous), strides in ELEMENTS for d1..d3, box {b0..b3}
 static bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box) {
+                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
-  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = elem_strides ? elem_strides[i] : 1; }
   for (int i = 0; i < rank - 1; ++i) gs[i] = strides_elems[i] * 2;
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(ptr), gd, gs, bx, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -581,6 +585,12 @@ struct FpropCall {
   int N, ks; bool b_mn; bool batched; bool flip_taps;
   const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias; int HW_rowbias;
   const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+  // --- optional generalisations (all zero = plain stride-1 conv) ---
+  int a_stride;            // 2: A is sampled at every other pixel (TMA elementStrides); a_H/a_W = dims of the A image
+  int a_H, a_W;
+  int ntap_override;       // > 0: explicit tap list instead of the ks*ks grid
+  int tap_dx[9], tap_dy[9], tap_z[9];
+  int64_t out_sn, out_sh, out_sw, out_off;  // output pixel addressing (0 = dense NHWC)
 };
 
 int fprop_supported(const FpropCall& c) {
@@ -608,17 +618,25 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   const int BN = (c.N % 128 == 0) ? 128 : 64;
   // K segments
   int nseg = 0, total = 0;
-  const int taps = c.ks * c.ks;
+  const int taps = c.ntap_override > 0 ? c.ntap_override : c.ks * c.ks;
   for (int t = 0; t < taps; ++t) {
     KSeg& s = p.seg[nseg++];
     s.a_src = 0; s.a_c0 = 0; s.nblk = c.Ca / 64;
-    int r = t / c.ks, q = t % c.ks;
-    s.dy = c.ks == 3 ? r - 1 : 0;
-    s.dx = c.ks == 3 ? q - 1 : 0;
-    if (c.flip_taps) { s.dy = -s.dy; s.dx = -s.dx; }  // dgrad: dX[q] = sum_tap dY[q - off(tap)] W[tap]^T
-    s.b_src = 0; s.b_k0 = 0; s.b_z = t;
+    if (c.ntap_override > 0) {
+      s.dx = c.tap_dx[t]; s.dy = c.tap_dy[t]; s.b_z = c.tap_z[t];
+    } else {
+      int r = t / c.ks, q = t % c.ks;
+      s.dy = c.ks == 3 ? r - 1 : 0;
+      s.dx = c.ks == 3 ? q - 1 : 0;
+      if (c.flip_taps) { s.dy = -s.dy; s.dx = -s.dx; }  // dgrad: dX[q] = sum_tap dY[q - off(tap)] W[tap]^T
+      s.b_z = t;
+    }
+    s.b_src = 0; s.b_k0 = 0;
     total += s.nblk;
   }
+  p.a_stride = c.a_stride > 1 ? c.a_stride : 1;
+  if (c.out_sn || c.out_sh || c.out_sw) { p.out_sn = c.out_sn; p.out_sh = c.out_sh; p.out_sw = c.out_sw; p.out_off = c.out_off; }
+  else { p.out_sn = (int64_t)c.H * c.W; p.out_sh = c.W; p.out_sw = 1; p.out_off = 0; }
   if (c.a2) {
     KSeg& s = p.seg[nseg++];
     s.a_src = 1; s.a_c0 = 0; s.nblk = c.Ca2 / 64; s.dx = s.dy = 0; s.b_src = 1; s.b_k0 = 0; s.b_z = 0;
@@ -636,13 +654,19 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   p.residual = (const __half*)c.residual; p.ld_res = c.ld_res; p.scale = c.scale;
   p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
   p.error_flag = error_flag();
+  p.dbg_shift = (int)env_u32("BD_UMMA_DBG_SHIFT", 0);
+  p.dbg_boff = (int)env_u32("BD_UMMA_DBG_BOFF", 0);
 
   CUtensorMap ma0, ma1, mb, mb1;
   {
-    uint64_t dims[4] = {(uint64_t)c.Ca, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
-    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)c.W * c.ld_a, (uint64_t)c.H * c.W * c.ld_a};
-    uint32_t box[4] = {64, (uint32_t)p.bw, (uint32_t)p.bh, (uint32_t)p.bn};
-    if (!make_map(&ma0, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
+    const int aH = c.a_stride > 1 ? c.a_H : c.H, aW = c.a_stride > 1 ? c.a_W : c.W;
+    const uint32_t st = (uint32_t)p.a_stride;
+    uint64_t dims[4] = {(uint64_t)c.Ca, (uint64_t)aW, (uint64_t)aH, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)aW * c.ld_a, (uint64_t)aH * aW * c.ld_a};
+    // with elementStrides s the box spans boxDim input elements and delivers ceil(boxDim / s) of them
+    uint32_t box[4] = {64, (uint32_t)p.bw * st, (uint32_t)p.bh * st, (uint32_t)p.bn};
+    uint32_t es[4] = {1, st, st, 1};
+    if (!make_map(&ma0, c.a, 4, dims, str, box, es)) return BD_ERR_CUDA;
   }
   if (c.a2) {
     uint64_t dims[4] = {(uint64_t)c.Ca2, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
@@ -683,6 +707,7 @@ struct WgradCall {
   int NB, H, W, ks; bool batched;
   void* y; int64_t ld_y; int out_mode;  // 0 atomic f32, 1 store f32, 2 store f16
   int zcount;                            // taps, or batch count
+  int b_stride, b_pad, b_H, b_W;         // stride-2 conv: B (= X) image dims / sampling stride / padding (0 = defaults)
 };
 
 int wgrad_supported(const WgradCall& c) {
@@ -721,6 +746,8 @@ int wgrad_launch(const WgradCall& c, cudaStream_t st) {
   p.kblocks_total = c.batched ? per_image : per_image * ceil_div(c.NB, p.pbn);
   p.ks = c.ks;
   p.batched = c.batched ? 1 : 0;
+  p.b_stride = c.b_stride > 1 ? c.b_stride : 1;
+  p.b_pad = c.b_stride > 1 ? c.b_pad : 1;
   p.Mtot = c.Mtot; p.Ntot = c.Ntot;
   const int BN = (c.Ntot % 128 == 0) ? 128 : 64;
   p.n_tiles = c.Ntot / BN;
@@ -749,9 +776,13 @@ int wgrad_launch(const WgradCall& c, cudaStream_t st) {
     if (!make_map(&ma, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
   }
   {
-    uint64_t dims[4] = {(uint64_t)c.Ntot, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
-    uint64_t str[3] = {(uint64_t)c.ld_b, (uint64_t)c.W * c.ld_b, (uint64_t)c.H * c.W * c.ld_b};
-    if (!make_map(&mb, c.b, 4, dims, str, box)) return BD_ERR_CUDA;
+    const int bH = c.b_stride > 1 ? c.b_H : c.H, bW = c.b_stride > 1 ? c.b_W : c.W;
+    const uint32_t st = (uint32_t)p.b_stride;
+    uint64_t dims[4] = {(uint64_t)c.Ntot, (uint64_t)bW, (uint64_t)bH, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_b, (uint64_t)bW * c.ld_b, (uint64_t)bH * bW * c.ld_b};
+    uint32_t bbox[4] = {64, (uint32_t)p.pbw * st, (uint32_t)p.pbh * st, (uint32_t)p.pbn};
+    uint32_t es[4] = {1, st, st, 1};
+    if (!make_map(&mb, c.b, 4, dims, str, bbox, es)) return BD_ERR_CUDA;
   }
   dim3 grid(m_tiles * p.n_tiles, c.zcount, splits);
   if (BN == 128) launch_wgrad_t<128>(ma, mb, p, grid, st); else launch_wgrad_t<64>(ma, mb, p, grid, st);

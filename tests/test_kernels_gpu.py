@@ -279,14 +279,16 @@ def test_conv_wgrad(ops, impl, B, H, Cin, Cout, k):
     assert rel_err(dw, 2 * refp) < 2e-3
 
 
-@pytest.mark.parametrize("pad", [0, 1])
-def test_conv_stride2(ops, pad):
-    """Downsample2D (resnet.py:199-208): padding=0 -> F.pad(0,1,0,1) first."""
-    B, H, Cc = 3, 16, 128
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("pad,B,H,Cc", [(0, 3, 16, 128), (1, 3, 16, 128), (0, 2, 32, 128), (0, 5, 8, 256)])
+def test_conv_stride2(ops, impl, pad, B, H, Cc):
+    """Downsample2D (resnet.py:199-208): padding=0 -> F.pad(0,1,0,1) first.  tcgen05 path: TMA elementStrides=2."""
+    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
     x, xr, w, wr = _conv_inputs(B, H, Cc, Cc, 3)
     bias = torch.randn(Cc, device="cuda")
     y = torch.empty(B, H // 2, H // 2, Cc, dtype=torch.half, device="cuda")
-    ops.conv_fwd(x, w, y, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad, bias=bias)
+    ops.conv_fwd(x, w, y, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad, bias=bias, impl=im)
+    assert ops.umma_error() == 0
     xin = xr.clone().requires_grad_(True)
     wq = wr.clone().requires_grad_(True)
     xp = F.pad(xin, (0, 1, 0, 1)) if pad == 0 else xin
@@ -296,13 +298,18 @@ def test_conv_stride2(ops, pad):
     dy32 = torch.randn_like(ref)
     dy, dyr = nhwc_half(dy32)
     ref.backward(dyr)
-    dx = torch.empty_like(x)
-    ops.conv_dgrad(dy, w, dx, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad)
-    assert (to_nchw(dx) - xin.grad).abs().max() < 3e-3 * max(1.0, float(xin.grad.abs().max()))
+    add32 = torch.randn_like(xr)
+    add, addr = nhwc_half(add32)
+    dx = add.clone()
+    ops.conv_dgrad(dy, w, dx, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad, residual=dx, impl=im)
+    assert ops.umma_error() == 0
+    assert (to_nchw(dx) - (xin.grad + addr)).abs().max() < 3e-3 * max(1.0, float(xin.grad.abs().max()))
     dw = torch.empty(9, Cc, Cc, device="cuda")
     db = torch.empty(Cc, device="cuda")
-    ops.conv_wgrad(x, dy, dw, db, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad)
+    ops.conv_wgrad(x, dy, dw, db, ksize=3, mode=ops.L.BD_CONV_S2_PAD01, pad=pad, impl=im)
+    assert ops.umma_error() == 0
     assert rel_err(dw, wq.grad.permute(2, 3, 0, 1).reshape(9, Cc, Cc)) < 2e-3
+    assert rel_err(db, dyr.sum((0, 2, 3))) < 2e-3
 
 
 def test_conv_in_out(ops):
