@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libb200bd.so")
 BD_OK, BD_ERR_INVALID, BD_ERR_CUDA, BD_ERR_UNSUPPORTED = 0, -1, -2, -3
 BD_CONV_S1, BD_CONV_S2_PAD01 = 0, 1
 BD_OUT_F16, BD_OUT_F32 = 0, 1
-BD_IMPL_AUTO, BD_IMPL_SIMT, BD_IMPL_UMMA = 0, 1, 2
+BD_IMPL_AUTO, BD_IMPL_SIMT, BD_IMPL_UMMA, BD_IMPL_UMMA_TILE = 0, 1, 2, 3
 
 vp, i64, i32, f32, u64, sz = C.c_void_p, C.c_int64, C.c_int, C.c_float, C.c_uint64, C.c_size_t
 

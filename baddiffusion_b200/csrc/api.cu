@@ -41,6 +41,18 @@ struct WgradCall {
   int zcount;
   int b_stride, b_pad, b_H, b_W;
 };
+struct Conv3Call {
+  const void* a; int64_t ld_a; int Ca;
+  const void* a2; int64_t ld_a2; int Ca2;
+  int NB, H, W;
+  const void* b; int64_t ld_b; int b_rows;
+  const void* b2; int64_t ld_b2;
+  int N; bool b_mn; bool flip;
+  const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias;
+  const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+};
+int conv3_supported(const Conv3Call& c);
+int conv3_launch(const Conv3Call& c, cudaStream_t st);
 int fprop_supported(const FpropCall& c);
 int fprop_launch(const FpropCall& c, cudaStream_t st);
 int wgrad_supported(const WgradCall& c);
@@ -156,12 +168,22 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
   }
   const bool s2ok = a->mode == BD_CONV_S1 || (a->H % 2 == 0 && a->W % 2 == 0 && !a->x2);
   const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
-  if (a->impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
+  if ((a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE) && !(can && bd_device_supported())) {
     set_error("bd_conv_fwd: tcgen05 path requested but shape unsupported (Cin=%d Cout=%d H=%d W=%d mode=%d)", a->Cin, a->Cout, a->H, a->W, a->mode);
     return BD_ERR_UNSUPPORTED;
   }
-  if (a->impl == BD_IMPL_UMMA || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
-    rc = umma::fprop_launch(c, st);
+  if (a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
+    umma::Conv3Call h;
+    memset(&h, 0, sizeof(h));
+    h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cin; h.a2 = a->x2; h.ld_a2 = a->ld_x2; h.Ca2 = a->Cin2;
+    h.NB = a->B; h.H = a->H; h.W = a->W; h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.b2 = a->w2; h.ld_b2 = a->Cin2;
+    h.N = a->Cout; h.b_mn = false; h.flip = false;
+    h.bias = a->bias; h.bias2 = a->bias2; h.rowbias = a->rowbias; h.ld_rowbias = a->ld_rowbias;
+    h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y; h.out_f32 = c.out_f32;
+    if (a->impl != BD_IMPL_UMMA_TILE && a->mode == BD_CONV_S1 && a->ksize == 3 && umma::conv3_supported(h))
+      rc = umma::conv3_launch(h, st);   // halo-reuse kernel (umma_conv3.cu)
+    else
+      rc = umma::fprop_launch(c, st);
     if (rc) return rc;
   } else {
     simt_conv_launch(a, false, st);
@@ -189,13 +211,21 @@ int bd_conv_dgrad(const bd_conv_args* a, void* stream) {
   if (s2) { c.H = Ho; c.W = Wo; }  // tiles run over the dY grid; each launch fills one parity class of dX
   const bool s2ok = !s2 || (a->H == 2 * Ho && a->W == 2 * Wo);
   const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
-  if (a->impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
+  if ((a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE) && !(can && bd_device_supported())) {
     set_error("bd_conv_dgrad: tcgen05 path requested but shape unsupported");
     return BD_ERR_UNSUPPORTED;
   }
-  if (a->impl == BD_IMPL_UMMA || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
+  if (a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
     if (!s2) {
-      rc = umma::fprop_launch(c, st);
+      umma::Conv3Call h;
+      memset(&h, 0, sizeof(h));
+      h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cout; h.NB = a->B; h.H = a->H; h.W = a->W;
+      h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.N = a->Cin; h.b_mn = true; h.flip = true;
+      h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y; h.out_f32 = c.out_f32;
+      if (a->impl != BD_IMPL_UMMA_TILE && a->ksize == 3 && umma::conv3_supported(h))
+        rc = umma::conv3_launch(h, st);
+      else
+        rc = umma::fprop_launch(c, st);
       if (rc) return rc;
     } else {
       // dX[2i+ah, 2j+aw] = sum over taps (r, s) with (ah + pad - r), (aw + pad - s) even of

@@ -10,13 +10,9 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
 // warps 2..5 = epilogue (tcgen05.ld -> bias / temb / residual -> global).  mbarrier ring of kStages stages.
-#include "common.cuh"
-
-#include <cuda.h>
+#include "umma_common.cuh"
 
 namespace bd {
-void count_launch(int n);
-
 namespace umma {
 
 constexpr int BM = 128;
@@ -80,99 +76,6 @@ struct WgradParams {
   int* error_flag;
 };
 
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
-__device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 2000000000LL) {  // ~1 s
-      if (error_flag) atomicExch(error_flag, code);
-      return false;
-    }
-  }
-  return true;
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_3d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2,
-                                            int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
-}
-
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
-}
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t lbo16, uint32_t sbo16) {
-  return (uint64_t)((smem_addr >> 4) & 0x3FFF) | ((uint64_t)(lbo16 & 0x3FFF) << 16) | ((uint64_t)(sbo16 & 0x3FFF) << 32) |
-         (1ull << 46) | (2ull << 61);
-}
-
 template <int BN, int kStages>
 struct Smem {
   static constexpr int kABytes = BM * BK * 2;
@@ -186,7 +89,7 @@ struct Smem {
 // fprop-style kernel
 // =============================================================================================
 template <int BN, int kStages, bool B_MN>
-__global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(320, 1) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                             const __grid_constant__ CUtensorMap tmA1,
                                                             const __grid_constant__ CUtensorMap tmB0,
                                                             const __grid_constant__ CUtensorMap tmB1,
@@ -277,8 +180,9 @@ __global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constan
       if (ok) umma_commit(tmem_full);
     }
   } else {
-    // ===== epilogue: 4 warps, warp (w % 4) owns TMEM lanes 32*(w%4) .. +31 =====
+    // ===== epilogue: 8 warps, warp w owns TMEM lanes 32*(w%4) .. +31 and column half (w-2)/4 =====
     const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int r = q * 32 + lane;  // row within the tile
     const int dn = r / (p.bw * p.bh), dh = (r / p.bw) % p.bh, dw = r % p.bw;
     const int n = n0 + dn, h = h0 + dh, w = w0 + dw;
@@ -288,62 +192,10 @@ __global__ void __launch_bounds__(192, 1) umma_fprop_kernel(const __grid_constan
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
     tc_fence_after();
     if (ok) {
-      const float* rb = (p.rowbias && valid) ? p.rowbias + (mlin / p.HW) * p.ld_rowbias : nullptr;
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c0, v);
-        if (valid) {
-          const int col = n_tile * BN + c0;
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-          if (p.bias) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col + j);
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          }
-          if (p.bias2) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(p.bias2 + col + j);
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          }
-          if (rb) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 b4 = *reinterpret_cast<const float4*>(rb + col + j);
-              f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-            }
-          }
-          if (p.residual) {
-            const __half* rr = p.residual + m * p.ld_res + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              float g[8];
-              unpack8(*reinterpret_cast<const half8*>(rr + j), g);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) f[j + k] += g[k];
-            }
-          }
-          if (p.scale != 1.0f) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] *= p.scale;
-          }
-          if (p.out_f32) {
-            float* yr = reinterpret_cast<float*>(p.y) + m * p.ld_y + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(yr + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-          } else {
-            __half* yr = reinterpret_cast<__half*>(p.y) + m * p.ld_y + col;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) *reinterpret_cast<half8*>(yr + j) = pack8(f + j);
-          }
-        }
-      }
+      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (BN / 2 + 4);  // operand stages are free now
+      EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+      epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
+                            n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
     }
   }
   tc_fence_before();
@@ -503,8 +355,8 @@ static PFN_encodeTiled get_encode() {
 }
 
 // rank-4 fp16 map: dims {d0,d1,d2,d3} (d0 contiguous), strides in ELEMENTS for d1..d3, box {b0..b3}
-static bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
-                     const uint32_t* box, const uint32_t* elem_strides = nullptr) {
+bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
+              const uint32_t* box, const uint32_t* elem_strides) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point unavailable"); return false; }
   cuuint64_t gd[5], gs[4];
@@ -533,7 +385,7 @@ int* error_flag() {
   return g_error_flag;
 }
 
-static uint32_t env_u32(const char* name, uint32_t dflt) {
+uint32_t env_u32(const char* name, uint32_t dflt) {
   const char* v = getenv(name);
   return v ? (uint32_t)strtoul(v, nullptr, 0) : dflt;
 }
@@ -568,7 +420,7 @@ static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_set = true;
   }
-  kern<<<grid, 192, L::kTotal, st>>>(a0, a1, b, b1, p);
+  kern<<<grid, 320, L::kTotal, st>>>(a0, a1, b, b1, p);
   count_launch(1);
   return 0;
 }

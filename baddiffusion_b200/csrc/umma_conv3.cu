@@ -1,0 +1,317 @@
+// 3x3 stride-1 convolution on tcgen05 with input-halo reuse ("conv3 halo kernel").
+//
+// One CTA computes a REGION of up to 4 MMA blocks (each 8 px wide x 16 rows = 128 pixels) x 128 output channels:
+// 4 accumulators of 128 columns fill the 512 TMEM columns of the SM.  Per 64-channel k-block
+//   * the input region plus its 1-pixel halo is fetched ONCE by a single TMA box {64 ch, rw+2, rh+2, rn} (out-of-
+//     bounds zero fill = conv padding) and stays in shared memory for all 9 taps: a tap is nothing but a different
+//     START ADDRESS of the UMMA A descriptor (row pitch = halo row, SBO = pitch * 128 B; the SWIZZLE_128B pattern is
+//     a function of the absolute smem address, so row-shifted views of one TMA-written tile are valid operands);
+//   * each tap's 128x64 weight tile streams through a small ring and is shared by the 4 blocks.
+// Shared-memory traffic from L2 per MAC drops ~5x against the one-tile-per-CTA kernel (umma.cu), which measured
+// L2->SM bound (361 TFLOP/s at 5.5 TB/s of operand traffic).  Used for conv fwd (K-major weights) and dgrad
+// (MN-major view of the same weights, taps flipped), with the fused 1x1-shortcut K segment and the same epilogue.
+#include "umma_common.cuh"
+
+namespace bd {
+namespace umma {
+
+constexpr int C3_BN = 128;
+constexpr int C3_BK = 64;
+constexpr int C3_MAXBLK = 4;
+constexpr int C3_ASTAGES = 2;
+constexpr int C3_BSTAGES = 3;
+constexpr int C3_A_STAGE_BYTES = 82 * 1024;           // >= 18*18*2*128 = 82,944 and 18*34*128 = 78,336
+constexpr int C3_B_STAGE_BYTES = C3_BN * C3_BK * 2;   // 16 KB
+constexpr int C3_BAR_OFFSET = C3_ASTAGES * C3_A_STAGE_BYTES + C3_BSTAGES * C3_B_STAGE_BYTES;
+constexpr int C3_SMEM = C3_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3_BSTAGES + 1) * 8 + 16 + 1024;
+
+struct Conv3Params {
+  int MB;                                   // MMA blocks in the region
+  int blk_row[C3_MAXBLK];                   // halo-row index of each block's pixel (0,0)
+  int blk_n[C3_MAXBLK], blk_h[C3_MAXBLK], blk_w[C3_MAXBLK];  // block origin inside the region
+  int pitch;                                // halo row pitch in pixels
+  int reg_w, reg_h, reg_n;                  // region extent
+  int tiles_w, tiles_h;                     // regions per image
+  int W, H, NB, HW, N;
+  int nkb, nkb2;                            // k-blocks of the 3x3 source / of the fused 1x1 source
+  int flip;                                 // dgrad: tap offsets negated
+  uint32_t a_bytes;                         // bytes of one halo box
+  uint32_t a_sbo, b_lbo, b_sbo, idesc;
+  const float* bias;
+  const float* bias2;
+  const float* rowbias;
+  int64_t ld_rowbias;
+  const __half* residual;
+  int64_t ld_res;
+  float scale;
+  void* y;
+  int64_t ld_y;
+  int out_f32;
+  int* error_flag;
+  long long* dbg;   // optional per-CTA timeline (64 slots per CTA), bring-up only
+};
+
+template <bool B_MN>
+__global__ void __launch_bounds__(320, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                            const __grid_constant__ CUtensorMap tmA1,
+                                                            const __grid_constant__ CUtensorMap tmB0,
+                                                            const __grid_constant__ CUtensorMap tmB1,
+                                                            const Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + C3_ASTAGES * C3_A_STAGE_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C3_BAR_OFFSET);
+  uint64_t* a_empty = a_full + C3_ASTAGES;
+  uint64_t* b_full = a_empty + C3_ASTAGES;
+  uint64_t* b_empty = b_full + C3_BSTAGES;
+  uint64_t* tmem_full = b_empty + C3_BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, n_tile = blockIdx.y;
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.reg_w, h0 = th * p.reg_h, n0 = tn * p.reg_n;
+  const int ncols = p.MB * C3_BN;  // 256 or 512 TMEM columns
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmB1);
+    for (int s = 0; s < C3_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C3_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, ncols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        const CUtensorMap* mapA = seg ? &tmA1 : &tmA0;
+        const CUtensorMap* mapB = seg ? &tmB1 : &tmB0;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_empty[as], aph ^ 1, p.error_flag, 1);
+          if (!ok) break;
+          mbar_expect_tx(&a_full[as], p.a_bytes);
+          tma_load_4d(mapA, &a_full[as], smem + as * C3_A_STAGE_BYTES, kb * C3_BK, w0 - 1, h0 - 1, n0);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_empty[bs], bph ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            uint8_t* sb = smem_b + bs * C3_B_STAGE_BYTES;
+            mbar_expect_tx(&b_full[bs], C3_B_STAGE_BYTES);
+            if (!B_MN) {
+              tma_load_3d(mapB, &b_full[bs], sb, kb * C3_BK, n_tile * C3_BN, t);
+            } else {
+              tma_load_3d(mapB, &b_full[bs], sb, n_tile * C3_BN, kb * C3_BK, t);
+              tma_load_3d(mapB, &b_full[bs], sb + 64 * C3_BK * 2, n_tile * C3_BN + 64, kb * C3_BK, t);
+            }
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true, first = true;
+      long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+      int di = 0;
+      if (dbg) dbg[di++] = clock64();
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_full[as], aph, p.error_flag, 2);
+          if (!ok) break;
+          if (dbg && di < 40) dbg[di++] = clock64();
+          const uint32_t sa = smem_u32(smem + as * C3_A_STAGE_BYTES);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_full[bs], bph, p.error_flag, 2);
+            if (!ok) break;
+            if (dbg && di < 40) dbg[di++] = clock64();
+            tc_fence_after();
+            int dy = seg ? 0 : t / 3 - 1, dx = seg ? 0 : t % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+            const uint32_t sb = smem_u32(smem_b + bs * C3_B_STAGE_BYTES);
+            const int tap_row = (dy + 1) * p.pitch + (dx + 1);
+            for (int mb = 0; mb < p.MB; ++mb) {
+              const uint32_t a0 = sa + (uint32_t)(p.blk_row[mb] + tap_row) * 128u;
+#pragma unroll
+              for (int k = 0; k < C3_BK / 16; ++k) {
+                const uint64_t ad = make_desc(a0 + k * 32, 1, p.a_sbo);
+                const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+                umma_f16(tmem_base + mb * C3_BN, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            umma_commit(&b_empty[bs]);
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (ok) umma_commit(&a_empty[as]);
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+      if (ok) umma_commit(tmem_full);
+      if (dbg) dbg[di++] = clock64();
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp w drains TMEM lanes 32*(w%4).. and column half (w-2)/4 of every block =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;          // row inside an MMA block: 8 px wide x 16 rows
+    const int dh = r >> 3, dw = r & 7;
+    const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
+    tc_fence_after();
+    long long* dbg = (p.dbg && warp == 2 && lane == 0) ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+    if (dbg) dbg[48] = clock64();
+    if (ok) {
+      // all MMAs have retired: the operand stages are free and serve as the fp32 staging tiles (one per warp)
+      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (C3_BN / 2 + 4);
+      EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+      for (int mb = 0; mb < p.MB; ++mb) {
+        const int n = n0 + p.blk_n[mb], h = h0 + p.blk_h[mb] + dh, w = w0 + p.blk_w[mb] + dw;
+        const bool valid = n < p.NB && h < p.H && w < p.W;
+        const int64_t m = ((int64_t)n * p.H + h) * p.W + w;
+        epilogue_warp<C3_BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + mb * C3_BN + half * (C3_BN / 2), stage, lane, m, m,
+                                 valid, n_tile * C3_BN + half * (C3_BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+      }
+    }
+  }
+  if (p.dbg && warp == 2 && lane == 0) p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 + 49] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, ncols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct Conv3Call {
+  const void* a; int64_t ld_a; int Ca;
+  const void* a2; int64_t ld_a2; int Ca2;     // fused 1x1 segment source (nullable)
+  int NB, H, W;
+  const void* b; int64_t ld_b; int b_rows;    // weights [9][b_rows][ld_b]
+  const void* b2; int64_t ld_b2;              // [N][Ca2]
+  int N; bool b_mn; bool flip;
+  const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias;
+  const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+};
+
+static bool conv3_geometry(int H, int W, Conv3Params* p) {
+  // region = 16 px wide; 32 rows of one image (H >= 32) or 16 rows of two images (H == 16)
+  if (W % 16 || H % 16) return false;
+  p->reg_w = 16;
+  p->pitch = 18;
+  if (H % 32 == 0) {
+    p->reg_h = 32; p->reg_n = 1; p->MB = 4;
+    for (int i = 0; i < 4; ++i) {
+      p->blk_n[i] = 0; p->blk_h[i] = (i >> 1) * 16; p->blk_w[i] = (i & 1) * 8;
+      p->blk_row[i] = p->blk_h[i] * p->pitch + p->blk_w[i];
+    }
+    p->a_bytes = 18u * 34u * 128u;
+  } else {
+    if (H != 16) return false;
+    p->reg_h = 16; p->reg_n = 2; p->MB = 4;
+    for (int i = 0; i < 4; ++i) {
+      p->blk_n[i] = i >> 1; p->blk_h[i] = 0; p->blk_w[i] = (i & 1) * 8;
+      p->blk_row[i] = p->blk_n[i] * (18 * p->pitch) + p->blk_w[i];
+    }
+    p->a_bytes = 18u * 18u * 2u * 128u;
+  }
+  p->tiles_w = W / p->reg_w;
+  p->tiles_h = H / p->reg_h;
+  return true;
+}
+
+int conv3_supported(const Conv3Call& c) {
+  Conv3Params p;
+  if (getenv("BD_NO_CONV3")) return 0;
+  if (c.Ca % 64 || (c.a2 && c.Ca2 % 64) || c.N % C3_BN) return 0;
+  if (c.ld_a % 8 || (c.a2 && c.ld_a2 % 8) || c.ld_b % 8 || c.ld_y % 8 || (c.residual && c.ld_res % 8)) return 0;
+  if (((uintptr_t)c.a & 15) || ((uintptr_t)c.b & 15) || (c.a2 && ((uintptr_t)c.a2 & 15))) return 0;
+  return conv3_geometry(c.H, c.W, &p) ? 1 : 0;
+}
+
+int conv3_launch(const Conv3Call& c, cudaStream_t st) {
+  Conv3Params p;
+  memset(&p, 0, sizeof(p));
+  if (!conv3_geometry(c.H, c.W, &p)) { set_error("conv3 halo kernel: unsupported geometry %dx%d", c.H, c.W); return BD_ERR_UNSUPPORTED; }
+  p.W = c.W; p.H = c.H; p.NB = c.NB; p.HW = c.H * c.W; p.N = c.N;
+  p.nkb = c.Ca / 64;
+  p.nkb2 = c.a2 ? c.Ca2 / 64 : 0;
+  p.flip = c.flip ? 1 : 0;
+  p.a_sbo = (uint32_t)(p.pitch * 128) >> 4;
+  if (c.b_mn) { p.b_lbo = 512; p.b_sbo = 64; } else { p.b_lbo = 1; p.b_sbo = 64; }
+  p.idesc = (1u << 4) | ((c.b_mn ? 1u : 0u) << 16) | ((uint32_t)(C3_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.bias = c.bias; p.bias2 = c.bias2; p.rowbias = c.rowbias; p.ld_rowbias = c.ld_rowbias;
+  p.residual = (const __half*)c.residual; p.ld_res = c.ld_res; p.scale = c.scale;
+  p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
+  p.error_flag = error_flag();
+  {
+    const char* e = getenv("BD_CONV3_DBG_PTR");  // device pointer of a (ctas x 64) int64 buffer, bring-up only
+    p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr;
+  }
+  CUtensorMap ma0, ma1, mb0, mb1;
+  const uint32_t box[4] = {64, (uint32_t)p.reg_w + 2, (uint32_t)p.reg_h + 2, (uint32_t)p.reg_n};
+  {
+    uint64_t dims[4] = {(uint64_t)c.Ca, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)c.W * c.ld_a, (uint64_t)c.H * c.W * c.ld_a};
+    if (!make_map(&ma0, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[4] = {(uint64_t)c.Ca2, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a2, (uint64_t)c.W * c.ld_a2, (uint64_t)c.H * c.W * c.ld_a2};
+    if (!make_map(&ma1, c.a2, 4, dims, str, box)) return BD_ERR_CUDA;
+  } else {
+    ma1 = ma0;
+  }
+  {
+    // K-major: [tap][N rows][K cols]; MN-major: [tap][K rows][N cols]
+    const int cols = c.b_mn ? c.N : c.Ca;
+    uint64_t dims[3] = {(uint64_t)cols, (uint64_t)c.b_rows, 9};
+    uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
+    uint32_t bbox[3] = {64, c.b_mn ? 64u : (uint32_t)C3_BN, 1};
+    if (!make_map(&mb0, c.b, 3, dims, str, bbox)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
+    uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
+    uint32_t bbox[3] = {64, (uint32_t)C3_BN, 1};
+    if (!make_map(&mb1, c.b2, 3, dims, str, bbox)) return BD_ERR_CUDA;
+  } else {
+    mb1 = mb0;
+  }
+  const int tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.reg_n);
+  dim3 grid(tiles, c.N / C3_BN);
+  static bool attr_set[2] = {false, false};
+  if (c.b_mn) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }
+    umma_conv3_kernel<true><<<grid, 320, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
+    umma_conv3_kernel<false><<<grid, 320, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+  }
+  count_launch(1);
+  return BD_OK;
+}
+
+}  // namespace umma
+}  // namespace bd

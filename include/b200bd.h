@@ -125,7 +125,12 @@ enum {
   BD_CONV_S2_PAD01 = 1 /* 3x3 stride 2 after F.pad(0,1,0,1) (Downsample2D, padding=0) or pad 1 (pad field) */
 };
 enum { BD_OUT_F16 = 0, BD_OUT_F32 = 1 };
-enum { BD_IMPL_AUTO = 0, BD_IMPL_SIMT = 1, BD_IMPL_UMMA = 2 };
+enum {
+  BD_IMPL_AUTO = 0,      /* tcgen05 when the shape tiles, CUDA cores otherwise                           */
+  BD_IMPL_SIMT = 1,      /* CUDA-core kernels                                                            */
+  BD_IMPL_UMMA = 2,      /* tcgen05 (halo-reuse 3x3 kernel where it applies, per-tile kernel otherwise)  */
+  BD_IMPL_UMMA_TILE = 3  /* tcgen05 per-tile implicit-GEMM kernel only (A re-fetched per tap)            */
+};
 
 typedef struct bd_conv_args {
   /* geometry: input (B,H,W,Cin) -> output (B,Ho,Wo,Cout); ksize 1 or 3 */

@@ -184,7 +184,7 @@ def test_groupnorm_fwd_bwd(ops, B, C, H, silu):
 # convolution: fwd / dgrad / wgrad, CUDA-core and tcgen05 paths
 # ------------------------------------------------------------------------------------------------
 CONV_CASES = [  # B, H, Cin, Cout, k
-    (2, 32, 128, 128, 3), (3, 16, 256, 256, 3), (4, 8, 256, 256, 3), (16, 4, 512, 256, 3), (5, 4, 256, 256, 3),
+    (2, 32, 128, 128, 3), (3, 16, 256, 256, 3), (1, 64, 128, 256, 3), (3, 16, 512, 128, 3), (4, 8, 256, 256, 3), (16, 4, 512, 256, 3), (5, 4, 256, 256, 3),
     (2, 32, 384, 128, 1), (2, 16, 128, 256, 3), (1, 64, 64, 64, 3),
 ]
 
@@ -198,10 +198,14 @@ def _conv_inputs(B, H, Cin, Cout, k, seed=0):
     return x, xr, w, wr
 
 
-@pytest.mark.parametrize("impl", ["simt", "umma"])
+def _impl(ops, name):
+    return {"simt": ops.L.BD_IMPL_SIMT, "umma": ops.L.BD_IMPL_UMMA, "umma_tile": ops.L.BD_IMPL_UMMA_TILE}[name]
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma", "umma_tile"])
 @pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
 def test_conv_fwd(ops, impl, B, H, Cin, Cout, k):
-    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    im = _impl(ops, impl)
     x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
     bias = torch.randn(Cout, device="cuda")
     rowbias = torch.randn(B, Cout, device="cuda")
@@ -220,12 +224,12 @@ def test_conv_fwd(ops, impl, B, H, Cin, Cout, k):
     assert (to_nchw(y32) - ref).abs().max() < 1e-3 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("impl", ["simt", "umma", "umma_tile"])
 def test_conv_fwd_fused_shortcut_and_views(ops, impl):
     """conv2 (3x3 over h) + conv_shortcut (1x1 over the concat input) in one accumulation; inputs and output are
     channel slices of wider buffers (the zero-copy torch.cat)."""
-    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
-    B, H, C1, C2, Cout = 2, 16, 256, 512, 256
+    im = _impl(ops, impl)
+    B, H, C1, C2, Cout = 3, 16, 256, 512, 256
     torch.manual_seed(1)
     hbuf = torch.randn(B, H, H, C1 + 64, device="cuda").half()
     xbuf = torch.randn(B, H, H, C2 + 128, device="cuda").half()
@@ -244,10 +248,10 @@ def test_conv_fwd_fused_shortcut_and_views(ops, impl):
     assert float(ybuf[..., :128].abs().max()) == 0.0  # neighbours of the slice untouched
 
 
-@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("impl", ["simt", "umma", "umma_tile"])
 @pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
 def test_conv_dgrad(ops, impl, B, H, Cin, Cout, k):
-    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    im = _impl(ops, impl)
     x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
     dy32 = torch.randn(B, Cout, H, H, device="cuda")
     dy, dyr = nhwc_half(dy32)
