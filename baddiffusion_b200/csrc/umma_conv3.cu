@@ -49,10 +49,11 @@ struct Conv3Params {
   int out_f32;
   int* error_flag;
   long long* dbg;   // optional per-CTA timeline (64 slots per CTA), bring-up only
+  int epi_mode;     // bring-up: 1 = skip global stores, 2 = skip phase 2, 3 = skip the whole epilogue
 };
 
 template <bool B_MN>
-__global__ void __launch_bounds__(320, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(576, 1) umma_conv3_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                             const __grid_constant__ CUtensorMap tmA1,
                                                             const __grid_constant__ CUtensorMap tmB0,
                                                             const __grid_constant__ CUtensorMap tmB1,
@@ -170,9 +171,9 @@ __global__ void __launch_bounds__(320, 1) umma_conv3_kernel(const __grid_constan
       if (dbg) dbg[di++] = clock64();
     }
   } else {
-    // ===== epilogue: 8 warps; warp w drains TMEM lanes 32*(w%4).. and column half (w-2)/4 of every block =====
+    // ===== epilogue: 16 warps; warp w drains TMEM lanes 32*(w%4).. and column quarter (w-2)/4 of every block =====
     const int q = warp & 3;
-    const int half = (warp - 2) >> 2;
+    const int half = (warp - 2) >> 2;   // 0..3: 32-column window
     const int r = q * 32 + lane;          // row inside an MMA block: 8 px wide x 16 rows
     const int dh = r >> 3, dw = r & 7;
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
@@ -181,14 +182,14 @@ __global__ void __launch_bounds__(320, 1) umma_conv3_kernel(const __grid_constan
     if (dbg) dbg[48] = clock64();
     if (ok) {
       // all MMAs have retired: the operand stages are free and serve as the fp32 staging tiles (one per warp)
-      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (C3_BN / 2 + 4);
+      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (C3_BN / 4 + 4);
       EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
       for (int mb = 0; mb < p.MB; ++mb) {
         const int n = n0 + p.blk_n[mb], h = h0 + p.blk_h[mb] + dh, w = w0 + p.blk_w[mb] + dw;
         const bool valid = n < p.NB && h < p.H && w < p.W;
         const int64_t m = ((int64_t)n * p.H + h) * p.W + w;
-        epilogue_warp<C3_BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + mb * C3_BN + half * (C3_BN / 2), stage, lane, m, m,
-                                 valid, n_tile * C3_BN + half * (C3_BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+        epilogue_warp<C3_BN / 4>(tmem_base + ((uint32_t)(q * 32) << 16) + mb * C3_BN + half * (C3_BN / 4), stage, lane, m, m,
+                                 valid, n_tile * C3_BN + half * (C3_BN / 4), e, p.rowbias, p.ld_rowbias, p.HW);
       }
     }
   }
@@ -250,6 +251,9 @@ int conv3_supported(const Conv3Call& c) {
   return conv3_geometry(c.H, c.W, &p) ? 1 : 0;
 }
 
+int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
+                  Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st);
+
 int conv3_launch(const Conv3Call& c, cudaStream_t st) {
   Conv3Params p;
   memset(&p, 0, sizeof(p));
@@ -268,6 +272,8 @@ int conv3_launch(const Conv3Call& c, cudaStream_t st) {
   {
     const char* e = getenv("BD_CONV3_DBG_PTR");  // device pointer of a (ctas x 64) int64 buffer, bring-up only
     p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr;
+    const char* m = getenv("BD_CONV3_EPI");
+    p.epi_mode = m ? atoi(m) : 0;
   }
   CUtensorMap ma0, ma1, mb0, mb1;
   const uint32_t box[4] = {64, (uint32_t)p.reg_w + 2, (uint32_t)p.reg_h + 2, (uint32_t)p.reg_n};
@@ -301,13 +307,232 @@ int conv3_launch(const Conv3Call& c, cudaStream_t st) {
   }
   const int tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.reg_n);
   dim3 grid(tiles, c.N / C3_BN);
+  if (p.reg_n == 1 && !getenv("BD_NO_CONV3T"))  // H % 32 == 0: weights-as-A / 256-pixel-B orientation
+    return conv3t_launch(ma0, ma1, mb0, mb1, p, c.b_mn, grid, st);
   static bool attr_set[2] = {false, false};
   if (c.b_mn) {
     if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }
-    umma_conv3_kernel<true><<<grid, 320, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    umma_conv3_kernel<true><<<grid, 576, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
-    umma_conv3_kernel<false><<<grid, 320, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    umma_conv3_kernel<false><<<grid, 576, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+  }
+  count_launch(1);
+  return BD_OK;
+}
+
+}  // namespace umma
+}  // namespace bd
+
+// =============================================================================================================
+// Transposed-orientation variant for images with H % 32 == 0:   D[cout, pixel] = W[cout, k] * X[pixel, k]^T
+//   A operand = the 128 x 64 weight tile of a tap (K-major for fwd, MN-major view of the same weights for dgrad),
+//   B operand = 256 pixels (8 px x 32 rows) of the resident halo tile, again addressed by a shifted descriptor.
+// A 128 x 256 x 16 MMA reads 4 KB (A) + 8 KB (B) of shared memory per 128 cycles = 96 B/cycle, which leaves headroom
+// under the 128 B/cycle shared-memory port; the 128 x 128 orientation needs all 128 B/cycle (measured 77 cycles per
+// MMA stand-alone, ~110 with the TMA writes of the pipeline in flight).  Two 256-column accumulators = 512 TMEM columns.
+// The epilogue transposes through shared memory: TMEM lanes are output channels, so each thread owns ONE channel of 32
+// pixels; it scatters them into a [pixel][channel] fp32 tile and the 4 warps of a group then write whole pixel rows.
+// =============================================================================================================
+namespace bd {
+namespace umma {
+
+constexpr int C3T_STAGE_FLOATS = 32 * (C3_BN + 4);  // one [32 pixels][128 channels] fp32 staging tile
+
+template <bool A_MN>
+__global__ void __launch_bounds__(576, 1) umma_conv3t_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                             const __grid_constant__ CUtensorMap tmX1,
+                                                             const __grid_constant__ CUtensorMap tmW0,
+                                                             const __grid_constant__ CUtensorMap tmW1,
+                                                             const Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem + C3_ASTAGES * C3_A_STAGE_BYTES;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C3_BAR_OFFSET);
+  uint64_t* a_empty = a_full + C3_ASTAGES;
+  uint64_t* b_full = a_empty + C3_ASTAGES;
+  uint64_t* b_empty = b_full + C3_BSTAGES;
+  uint64_t* tmem_full = b_empty + C3_BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x, n_tile = blockIdx.y;
+  const int tw = tile % p.tiles_w, th = (tile / p.tiles_w) % p.tiles_h, tn = tile / (p.tiles_w * p.tiles_h);
+  const int w0 = tw * p.reg_w, h0 = th * p.reg_h, n0 = tn;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmX1);
+    prefetch_tmap(&tmW0);
+    prefetch_tmap(&tmW1);
+    for (int s = 0; s < C3_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C3_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        const CUtensorMap* mapX = seg ? &tmX1 : &tmX0;
+        const CUtensorMap* mapW = seg ? &tmW1 : &tmW0;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_empty[as], aph ^ 1, p.error_flag, 1);
+          if (!ok) break;
+          mbar_expect_tx(&a_full[as], p.a_bytes);
+          tma_load_4d(mapX, &a_full[as], smem + as * C3_A_STAGE_BYTES, kb * C3_BK, w0 - 1, h0 - 1, n0);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_empty[bs], bph ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            uint8_t* sw = smem_w + bs * C3_B_STAGE_BYTES;
+            mbar_expect_tx(&b_full[bs], C3_B_STAGE_BYTES);
+            if (!A_MN) {
+              tma_load_3d(mapW, &b_full[bs], sw, kb * C3_BK, n_tile * C3_BN, t);
+            } else {
+              tma_load_3d(mapW, &b_full[bs], sw, n_tile * C3_BN, kb * C3_BK, t);
+              tma_load_3d(mapW, &b_full[bs], sw + 64 * C3_BK * 2, n_tile * C3_BN + 64, kb * C3_BK, t);
+            }
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true, first = true;
+      long long* dbg = p.dbg ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+      int di = 0;
+      if (dbg) dbg[di++] = clock64();
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_full[as], aph, p.error_flag, 2);
+          if (!ok) break;
+          if (dbg && di < 40) dbg[di++] = clock64();
+          const uint32_t sx = smem_u32(smem + as * C3_A_STAGE_BYTES);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_full[bs], bph, p.error_flag, 2);
+            if (!ok) break;
+            if (dbg && di < 40) dbg[di++] = clock64();
+            tc_fence_after();
+            int dy = seg ? 0 : t / 3 - 1, dx = seg ? 0 : t % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+            const uint32_t sw = smem_u32(smem_w + bs * C3_B_STAGE_BYTES);
+            const int tap_row = (dy + 1) * p.pitch + (dx + 1);
+#pragma unroll
+            for (int blk = 0; blk < 2; ++blk) {
+              const uint32_t x0 = sx + (uint32_t)(blk * 8 + tap_row) * 128u;
+#pragma unroll
+              for (int k = 0; k < C3_BK / 16; ++k) {
+                const uint64_t wd = A_MN ? make_desc(sw + k * 2048, 512, 64) : make_desc(sw + k * 32, 1, 64);
+                const uint64_t xd = make_desc(x0 + k * 32, 1, p.a_sbo);
+                umma_f16(tmem_base + blk * 256, wd, xd, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            umma_commit(&b_empty[bs]);
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (ok) umma_commit(&a_empty[as]);
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+      if (ok) umma_commit(tmem_full);
+      if (dbg) dbg[di++] = clock64();
+    }
+  } else {
+    // ===== transposing epilogue: 4 groups of 4 warps; group g drains pixel half (g&1) of block (g>>1); warp quadrant
+    // q owns channels 32q.. =====
+    const int q = warp & 3, grp4 = (warp - 2) >> 2, grp = grp4 >> 1, phalf = grp4 & 1;
+    const int tid_g = ((warp - 2) & 3) * 32 + lane;  // 0..127 inside the group
+    const int ch = q * 32 + lane;                    // output channel inside the 128-wide n tile
+    const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
+    tc_fence_after();
+    long long* dbg = (p.dbg && warp == 2 && lane == 0) ? p.dbg + (size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 : nullptr;
+    if (dbg) dbg[48] = clock64();
+    if (ok) {
+      float* stage0 = reinterpret_cast<float*>(smem) + grp4 * 2 * C3T_STAGE_FLOATS;
+      const int gcol = n_tile * C3_BN + ch;
+      float badd = 0.f;
+      if (p.bias) badd += p.bias[gcol];
+      if (p.bias2) badd += p.bias2[gcol];
+      if (p.rowbias) badd += p.rowbias[(int64_t)n0 * p.ld_rowbias + gcol];
+      const int piece = tid_g & 15, rbase = tid_g >> 4;  // phase 2: 8 channels of rows rbase, rbase+8, ...
+      const int col = n_tile * C3_BN + piece * 8;
+#pragma unroll 1
+      for (int j0 = phalf * 128; j0 < phalf * 128 + 128 && p.epi_mode < 3; j0 += 32) {
+        float* stage = stage0 + ((j0 >> 5) & 1) * C3T_STAGE_FLOATS;
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + grp * 256 + j0, v);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) stage[jj * (C3_BN + 4) + ch] = __uint_as_float(v[jj]) + badd;
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + grp4) : "memory");
+        if (p.epi_mode == 2) continue;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = rbase + 8 * i;           // pixel inside the chunk
+          const int j = j0 + row;                  // pixel inside the block: 8 px x 32 rows
+          const int h = h0 + (j >> 3), w = w0 + grp * 8 + (j & 7);
+          const int64_t m = ((int64_t)n0 * p.H + h) * p.W + w;
+          const float* sp = stage + row * (C3_BN + 4) + piece * 8;
+          const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
+          float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+          if (p.residual) {
+            float g[8];
+            unpack8(*reinterpret_cast<const half8*>(p.residual + m * p.ld_res + col), g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] += g[k];
+          }
+          if (p.scale != 1.0f) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] *= p.scale;
+          }
+          if (p.epi_mode == 1 && f[0] != 12345.678f) continue;
+          if (p.out_f32) {
+            float* yr = reinterpret_cast<float*>(p.y) + m * p.ld_y + col;
+            *reinterpret_cast<float4*>(yr) = make_float4(f[0], f[1], f[2], f[3]);
+            *reinterpret_cast<float4*>(yr + 4) = make_float4(f[4], f[5], f[6], f[7]);
+          } else {
+            *reinterpret_cast<half8*>(reinterpret_cast<__half*>(p.y) + m * p.ld_y + col) = pack8(f);
+          }
+        }
+      }
+    }
+  }
+  if (p.dbg && warp == 2 && lane == 0) p.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 64 + 49] = clock64();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
+                  Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st) {
+  p.idesc = (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static bool attr_set[2] = {false, false};
+  if (a_mn) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }
+    umma_conv3t_kernel<true><<<grid, 576, C3_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
+    umma_conv3t_kernel<false><<<grid, 576, C3_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
   }
   count_launch(1);
   return BD_OK;
