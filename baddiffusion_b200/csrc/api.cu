@@ -51,6 +51,14 @@ struct Conv3Call {
   const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias;
   const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
 };
+struct Wgrad3Call {
+  const void* dy; int64_t ld_dy; int Cout;
+  const void* x; int64_t ld_x; int Cin;
+  int NB, H, W;
+  float* dw;
+};
+int wgrad3_supported(const Wgrad3Call& c);
+int wgrad3_launch(const Wgrad3Call& c, cudaStream_t st);
 int conv3_supported(const Conv3Call& c);
 int conv3_launch(const Conv3Call& c, cudaStream_t st);
 int fprop_supported(const FpropCall& c);
@@ -277,17 +285,22 @@ int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, fl
     npix = (int64_t)B * Ho * Wo;
   }
   const bool can = s2ok && umma::wgrad_supported(c);
-  if (impl == BD_IMPL_UMMA && !(can && bd_device_supported())) {
+  if ((impl == BD_IMPL_UMMA || impl == BD_IMPL_UMMA_TILE) && !(can && bd_device_supported())) {
     set_error("bd_conv_wgrad: tcgen05 path requested but shape unsupported");
     return BD_ERR_UNSUPPORTED;
   }
-  if (impl == BD_IMPL_UMMA || (impl == BD_IMPL_AUTO && can && umma_allowed())) {
+  if (impl == BD_IMPL_UMMA || impl == BD_IMPL_UMMA_TILE || (impl == BD_IMPL_AUTO && can && umma_allowed())) {
     const size_t n = (size_t)Cout * Cin * ksize * ksize;
     if (!accumulate) {
       zero_f32_kernel<<<ceil_div(n, 2048), 256, 0, st>>>(dw, n);
       count_launch(1);
     }
-    int rc = umma::wgrad_launch(c, st);
+    umma::Wgrad3Call w3{dy, ld_dy, Cout, x, ld_x, Cin, B, H, W, dw};
+    int rc;
+    if (impl != BD_IMPL_UMMA_TILE && mode == BD_CONV_S1 && ksize == 3 && umma::wgrad3_supported(w3))
+      rc = umma::wgrad3_launch(w3, st);   // 3 taps per CTA sharing one dY / X-halo tile (umma_wgrad3.cu)
+    else
+      rc = umma::wgrad_launch(c, st);
     if (rc) return rc;
     if (dbias) {
       rc = bd_colsum_f16(dy, ld_dy, dbias, 0, 1, npix, Cout, accumulate, stream);

@@ -1,6 +1,7 @@
 // GroupNorm (+SiLU) forward / backward on fp16 NHWC views with fp32/fp64 statistics (K4/K5).
 // HBM-bound: forward reads x twice (the second read is L2-resident at the UNet's sizes) and writes y once.
-// Reductions are two-stage with a fixed summation order => bitwise reproducible run to run.
+// Statistics are reduced in two stages with a fixed summation order (bitwise reproducible); the parameter gradients
+// dgamma / dbeta are accumulated across samples with fp32 atomics (one per sample and channel).
 // Thread mapping (all kernels): block = C8 * rows threads, C8 = C/8; a thread owns ONE 8-channel vector
 // (v = tid % C8) for its whole life, so per-channel parameters live in registers and every warp reads
 // consecutive 16-byte vectors of a pixel row (coalesced); pixels are strided by `rows` with 4 loads in flight.
@@ -209,21 +210,32 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
   }
 }
 
-// per (b, g): gA = sum_c gamma*s1 / n, gB = sum_c gamma*s2 / n  -> gab (B, G, 2); one block per sample
-__global__ void gn_bwd_group_kernel(const float* __restrict__ work, const float* __restrict__ gamma,
-                                    float* __restrict__ gab, int HW, int C, int G, int splits) {
+// per sample b: (1) channel sums over the split partials -> dgamma / dbeta contribution (fp32 atomics: one per
+// (sample, channel)), (2) per-group gA = sum_c gamma*s1 / n, gB = sum_c gamma*s2 / n -> gab (B, G, 2).
+// smem: cs[2][C]
+__global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restrict__ work, const float* __restrict__ gamma,
+                                                           float* __restrict__ gab, float* __restrict__ dgamma,
+                                                           float* __restrict__ dbeta, int HW, int C, int G, int splits) {
+  extern __shared__ float cs[];
   const int b = blockIdx.x, cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int sp = 0; sp < splits; ++sp) {
+      const float* w = work + (((int64_t)b * splits + sp) * 2) * C;
+      s1 += w[c];
+      s2 += w[C + c];
+    }
+    cs[c] = s1;
+    cs[C + c] = s2;
+    atomicAdd(dbeta + c, s1);
+    atomicAdd(dgamma + c, s2);
+  }
+  __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double a = 0.0, q = 0.0;
     for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      double s1 = 0.0, s2 = 0.0;
-      for (int sp = 0; sp < splits; ++sp) {
-        const float* w = work + (((int64_t)b * splits + sp) * 2) * C;
-        s1 += (double)w[c];
-        s2 += (double)w[C + c];
-      }
-      a += (double)gamma[c] * s1;
-      q += (double)gamma[c] * s2;
+      a += (double)gamma[c] * (double)cs[c];
+      q += (double)gamma[c] * (double)cs[C + c];
     }
     const double n = (double)HW * cpg;
     gab[((int64_t)b * G + g) * 2 + 0] = (float)(a / n);
@@ -273,30 +285,6 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
       }
       *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
     }
-  }
-}
-
-// dgamma[c] (+)= sum_{b,split} s2 ; dbeta[c] (+)= sum s1.  block (32 channels x 8 row lanes), fixed order.
-__global__ void __launch_bounds__(256) gn_bwd_params_kernel(const float* __restrict__ work, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int BS, int C, int accumulate) {
-  __shared__ float r1[8][33], r2[8][33];
-  const int cl = threadIdx.x & 31, lane_r = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + cl;
-  float s1 = 0.f, s2 = 0.f;
-  if (c < C)
-    for (int i = lane_r; i < BS; i += 8) {
-      s1 += work[(int64_t)i * 2 * C + c];
-      s2 += work[(int64_t)i * 2 * C + C + c];
-    }
-  r1[lane_r][cl] = s1;
-  r2[lane_r][cl] = s2;
-  __syncthreads();
-  if (lane_r == 0 && c < C) {
-    float a = 0.f, q = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) { a += r1[i][cl]; q += r2[i][cl]; }
-    dgamma[c] = (accumulate ? dgamma[c] : 0.f) + q;
-    dbeta[c] = (accumulate ? dbeta[c] : 0.f) + a;
   }
 }
 
@@ -354,12 +342,11 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu);
   // group sums live right behind the per-split partials in the workspace
   float* gab = work + (size_t)B * splits * 2 * C;
-  gn_bwd_group_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(work, gamma, gab, HW, C, G, splits);
+  gn_bwd_group_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(work, gamma, gab, dgamma, dbeta, HW, C, G, splits);
   gn_bwd_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
       stats, gab, HW, C, G, asplits, apply_silu);
-  gn_bwd_params_kernel<<<ceil_div(C, 32), 256, 0, (cudaStream_t)stream>>>(work, dgamma, dbeta, B * splits, C, 1);
-  count_launch(4);
+  count_launch(3);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }

@@ -109,8 +109,8 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
 size_t bd_gn_workspace_floats(int B, int G);
 int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
                      float* stats, float* work, int B, int HW, int C, int G, float eps, int apply_silu, void* stream);
-/* backward: dx = GN'(dy (* SiLU')) [+ add_dx]; dgamma/dbeta f32 (B-reduced, accumulated if accumulate!=0).
- * dgb_work: (B, 2, C) f32 scratch.                                                                    */
+/* backward: dx = GN'(dy (* SiLU')) [+ add_dx]; dgamma / dbeta f32 are ACCUMULATED into (zero them first).
+ * work: bd_gn_workspace_floats(B, C) floats.                                                          */
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
                      float* dbeta, float* dgb_work, int B, int HW, int C, int G, int apply_silu, void* stream);

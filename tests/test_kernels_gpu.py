@@ -264,10 +264,10 @@ def test_conv_dgrad(ops, impl, B, H, Cin, Cout, k):
     assert (to_nchw(dx) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
 
 
-@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("impl", ["simt", "umma", "umma_tile"])
 @pytest.mark.parametrize("B,H,Cin,Cout,k", CONV_CASES)
 def test_conv_wgrad(ops, impl, B, H, Cin, Cout, k):
-    im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
+    im = _impl(ops, impl)
     x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, k)
     dy32 = torch.randn(B, Cout, H, H, device="cuda")
     dy, dyr = nhwc_half(dy32)
