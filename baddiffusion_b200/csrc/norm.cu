@@ -64,8 +64,10 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float
   }
 }
 
-__device__ __forceinline__ void gn_finalize_stats(const float* __restrict__ work, float* sm_mean, float* sm_rstd,
-                                                  int b, int G, int splits, int HW, int cpg, float eps) {
+// one block per sample: (mean, rstd) per group from the split partials, fixed order, double accumulation
+__global__ void gn_finalize_kernel(const float* __restrict__ work, float* __restrict__ stats, int G, int splits, int HW,
+                                   int cpg, float eps) {
+  const int b = blockIdx.x;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double ds = 0.0, dq = 0.0;
     for (int sp = 0; sp < splits; ++sp) {
@@ -73,39 +75,29 @@ __device__ __forceinline__ void gn_finalize_stats(const float* __restrict__ work
       ds += (double)w[0];
       dq += (double)w[1];
     }
-    double n = (double)HW * cpg;
-    double mean = ds / n;
+    const double n = (double)HW * cpg;
+    const double mean = ds / n;
     double var = dq / n - mean * mean;
     if (var < 0.0) var = 0.0;
-    sm_mean[g] = (float)mean;
-    sm_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    stats[((int64_t)b * G + g) * 2 + 0] = (float)mean;
+    stats[((int64_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
   }
 }
 
-// block = C8 * rows threads; smem: mean[G], rstd[G]
-__global__ void gn_apply_kernel(const __half* __restrict__ x, int64_t ldx, __half* __restrict__ y, int64_t ldy,
-                                const float* __restrict__ gamma, const float* __restrict__ beta,
-                                const float* __restrict__ work, float* __restrict__ stats, int HW, int C, int G,
-                                int splits, int asplits, float eps, int apply_silu) {
-  extern __shared__ float sm[];
-  float* sm_mean = sm;
-  float* sm_rstd = sm + G;
+// block = C8 * rows threads.  y = x * a + c  with a = rstd*gamma, c = beta - mean*a (per channel, in registers)
+__global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restrict__ x, int64_t ldx,
+                                                          __half* __restrict__ y, int64_t ldy,
+                                                          const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                          const float* __restrict__ stats, int HW, int C, int G,
+                                                          int asplits, int apply_silu) {
   const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
-  gn_finalize_stats(work, sm_mean, sm_rstd, b, G, splits, HW, cpg, eps);
-  __syncthreads();
-  if (blockIdx.x == 0 && stats)
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      stats[((int64_t)b * G + g) * 2 + 0] = sm_mean[g];
-      stats[((int64_t)b * G + g) * 2 + 1] = sm_rstd[g];
-    }
-  // y = x * a + c  with a = rstd*gamma, c = beta - mean*rstd*gamma (per channel, in registers)
   float a[8], c[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = v * 8 + k, g = ch / cpg;
-    a[k] = sm_rstd[g] * gamma[ch];
-    c[k] = beta[ch] - sm_mean[g] * a[k];
+    a[k] = stats[((int64_t)b * G + g) * 2 + 1] * gamma[ch];
+    c[k] = beta[ch] - stats[((int64_t)b * G + g) * 2 + 0] * a[k];
   }
   const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
@@ -305,7 +297,7 @@ static inline void gn_geometry(int B, int HW, int C, int* threads, int* rows, in
   *threads = C8 * (*rows);
   *splits = gn_splits(B, HW, *rows);
   // the apply passes have no reduction: give them ~8 blocks per SM
-  int want = ceil_div(8 * num_sms(), B);
+  int want = ceil_div(4 * num_sms(), B);
   int cap = HW / (*rows) > 0 ? HW / (*rows) : 1;
   *asplits = want < cap ? want : cap;
   if (*asplits < 1) *asplits = 1;
@@ -321,9 +313,12 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
   gn_geometry(B, HW, C, &threads, &rows, &splits, &asplits);
   gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, work, HW, C, G, splits);
-  gn_apply_kernel<<<dim3(asplits, B), threads, 2 * G * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, work, stats, HW, C, G, splits, asplits, eps, apply_silu);
-  count_launch(2);
+  // stats may be omitted by inference callers: park them behind the partials
+  float* st = stats ? stats : work + (size_t)B * splits * 2 * C;
+  gn_finalize_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(work, st, G, splits, HW, C / G, eps);
+  gn_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, st, HW, C, G, asplits, apply_silu);
+  count_launch(3);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }

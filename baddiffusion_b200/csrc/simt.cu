@@ -395,46 +395,53 @@ __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restric
   }
 }
 
-// conv_in wgrad: dW[co][ci][tap] += sum_p dY[p][co] x[src]; thread = co, Cin*9 (<= 36) accumulators
+// conv_in wgrad: dW[tap][co][ci] += sum_p dY[p][co] x[ci][src(p,tap)].  thread = (co, pixel lane); the Cin*9 (<= 36)
+// input taps of a pixel are warp-uniform broadcast loads; block partials meet in shared memory, then one global atomic
+// per output and block.
 template <int KMAX>
 __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dy,
                                                             int64_t lddy, float* __restrict__ dw,
                                                             float* __restrict__ dbias, int B, int Cin, int H, int W,
                                                             int Cout) {
+  extern __shared__ float sacc[];  // [Cout][K] + bias[Cout]
   const int K = Cin * 9;
+  for (int i = threadIdx.x; i < Cout * (K + 1); i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
   const int64_t P = (int64_t)B * H * W;
   const int64_t chunk = (P + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * chunk, p1 = p0 + chunk < P ? p0 + chunk : P;
-  __shared__ float sx[KMAX];
-  for (int co = threadIdx.x; co < ((Cout + 255) / 256) * 256; co += blockDim.x) {
+  const int lanes_p = blockDim.x / Cout > 0 ? blockDim.x / Cout : 1;
+  const int co = threadIdx.x % Cout, pl = threadIdx.x / Cout;
+  if (pl < lanes_p && threadIdx.x < lanes_p * Cout) {
     float acc[KMAX], bacc = 0.f;
 #pragma unroll
     for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-    for (int64_t p = p0; p < p1; ++p) {
+    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
       const int ww = (int)(p % W);
       const int64_t q = p / W;
       const int hh = (int)(q % H), b = (int)(q / H);
-      __syncthreads();
-      if (threadIdx.x < K) {
-        int ci = threadIdx.x / 9, tap = threadIdx.x % 9;
-        int sh = hh + tap / 3 - 1, sxx = ww + tap % 3 - 1;
-        sx[threadIdx.x] = (sh >= 0 && sh < H && sxx >= 0 && sxx < W) ? x[(((int64_t)b * Cin + ci) * H + sh) * W + sxx] : 0.f;
-      }
-      __syncthreads();
-      if (co < Cout) {
-        float d = __half2float(dy[p * lddy + co]);
-        bacc += d;
+      const float d = __half2float(dy[p * lddy + co]);
+      bacc += d;
 #pragma unroll
-        for (int k = 0; k < KMAX; ++k)
-          if (k < K) acc[k] = fmaf(d, sx[k], acc[k]);
+      for (int k = 0; k < KMAX; ++k) {
+        if (k < K) {
+          const int ci = k / 9, tap = k % 9;
+          const int sh = hh + tap / 3 - 1, sx = ww + tap % 3 - 1;
+          const float xv = (sh >= 0 && sh < H && sx >= 0 && sx < W) ? __ldg(x + (((int64_t)b * Cin + ci) * H + sh) * W + sx) : 0.f;
+          acc[k] = fmaf(d, xv, acc[k]);
+        }
       }
     }
-    if (co < Cout) {
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k)
-        if (k < K) atomicAdd(dw + ((int64_t)(k % 9) * Cout + co) * Cin + k / 9, acc[k]);
-      if (dbias) atomicAdd(dbias + co, bacc);
-    }
+    for (int k = 0; k < KMAX; ++k)
+      if (k < K) atomicAdd(&sacc[co * (K + 1) + k], acc[k]);
+    atomicAdd(&sacc[co * (K + 1) + K], bacc);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < Cout * (K + 1); i += blockDim.x) {
+    const int c = i / (K + 1), k = i % (K + 1);
+    if (k < K) atomicAdd(dw + ((int64_t)(k % 9) * Cout + c) * Cin + k / 9, sacc[i]);
+    else if (dbias) atomicAdd(dbias + c, sacc[i]);
   }
 }
 
@@ -504,43 +511,71 @@ __global__ void __launch_bounds__(256) conv_out_dgrad_kernel(const float* __rest
   }
 }
 
-// conv_out wgrad: dW[co][ci][tap] += sum_p dY[co][p] X[src(p,tap)][ci]; thread = ci, Cout*9 (<= 36) accumulators
+// conv_out wgrad: dW[tap][co][ci] += sum_p dY[co][p] X[src(p,tap)][ci].  thread = (4-channel quad, pixel lane): a
+// warp reads whole pixel rows (coalesced); Cout*9 (<= 36) x 4 accumulators per thread; shared-memory then global atomics.
 template <int KMAX>
 __global__ void __launch_bounds__(256) conv_out_wgrad_kernel(const __half* __restrict__ x, int64_t ldx,
                                                              const float* __restrict__ dy, float* __restrict__ dw,
                                                              float* __restrict__ dbias, int B, int Cin, int H, int W,
                                                              int Cout) {
+  extern __shared__ float sacc[];  // [9*Cout][Cin] + bias[4]
+  const int nout = 9 * Cout * Cin;
+  for (int i = threadIdx.x; i < nout + 4; i += blockDim.x) sacc[i] = 0.f;
+  __syncthreads();
   const int64_t P = (int64_t)B * H * W;
   const int64_t chunk = (P + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * chunk, p1 = p0 + chunk < P ? p0 + chunk : P;
-  for (int ci = threadIdx.x; ci < Cin; ci += blockDim.x) {
-    float acc[KMAX];
+  const int nq = Cin / 4, lanes_p = blockDim.x / nq;
+  const int qd = threadIdx.x % nq, pl = threadIdx.x / nq;
+  if (pl < lanes_p) {
+    float acc[KMAX][4];
     float bacc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-    for (int64_t p = p0; p < p1; ++p) {
+    for (int k = 0; k < KMAX; ++k) acc[k][0] = acc[k][1] = acc[k][2] = acc[k][3] = 0.f;
+    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
       const int ww = (int)(p % W);
       const int64_t q = p / W;
       const int hh = (int)(q % H), b = (int)(q / H);
       float d[4] = {0.f, 0.f, 0.f, 0.f};
-      for (int co = 0; co < Cout; ++co) d[co] = dy[(((int64_t)b * Cout + co) * H + hh) * W + ww];
-      if (ci == 0)
-        for (int co = 0; co < Cout; ++co) bacc[co] += d[co];
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+        if (co < Cout) d[co] = __ldg(dy + (((int64_t)b * Cout + co) * H + hh) * W + ww);
+      if (qd == 0) {
+#pragma unroll
+        for (int co = 0; co < 4; ++co) bacc[co] += d[co];
+      }
 #pragma unroll
       for (int tap = 0; tap < 9; ++tap) {
-        int sh = hh + tap / 3 - 1, sx = ww + tap % 3 - 1;
+        const int sh = hh + tap / 3 - 1, sx = ww + tap % 3 - 1;
         if (sh < 0 || sh >= H || sx < 0 || sx >= W) continue;
-        float xv = __half2float(x[(((int64_t)b * H + sh) * W + sx) * ldx + ci]);
+        const __half2* hp = reinterpret_cast<const __half2*>(x + (((int64_t)b * H + sh) * W + sx) * ldx + qd * 4);
+        const float2 f0 = __half22float2(hp[0]), f1 = __half22float2(hp[1]);
 #pragma unroll
         for (int co = 0; co < 4; ++co)
-          if (co * 9 + tap < KMAX && co < Cout) acc[co * 9 + tap] = fmaf(d[co], xv, acc[co * 9 + tap]);
+          if (co * 9 + tap < KMAX) {
+            acc[co * 9 + tap][0] = fmaf(d[co], f0.x, acc[co * 9 + tap][0]);
+            acc[co * 9 + tap][1] = fmaf(d[co], f0.y, acc[co * 9 + tap][1]);
+            acc[co * 9 + tap][2] = fmaf(d[co], f1.x, acc[co * 9 + tap][2]);
+            acc[co * 9 + tap][3] = fmaf(d[co], f1.y, acc[co * 9 + tap][3]);
+          }
       }
     }
-    for (int co = 0; co < Cout; ++co)
-      for (int tap = 0; tap < 9; ++tap) atomicAdd(dw + ((int64_t)tap * Cout + co) * Cin + ci, acc[co * 9 + tap]);
-    if (ci == 0 && dbias)
-      for (int co = 0; co < Cout; ++co) atomicAdd(dbias + co, bacc[co]);
+#pragma unroll
+    for (int co = 0; co < 4; ++co)
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (co < Cout && co * 9 + tap < KMAX) atomicAdd(&sacc[(tap * Cout + co) * Cin + qd * 4 + e], acc[co * 9 + tap][e]);
+    if (qd == 0) {
+#pragma unroll
+      for (int co = 0; co < 4; ++co)
+        if (co < Cout) atomicAdd(&sacc[nout + co], bacc[co]);
+    }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < nout; i += blockDim.x) atomicAdd(dw + i, sacc[i]);
+  if (dbias && threadIdx.x < Cout) atomicAdd(dbias + threadIdx.x, sacc[nout + threadIdx.x]);
 }
 
 __global__ void zero_f32_kernel(float* p, size_t n) {
@@ -671,7 +706,8 @@ int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* 
     if (dbias) zero_f32_kernel<<<1, 256, 0, st>>>(dbias, Cout);
     count_launch(2);
   }
-  conv_in_wgrad_kernel<36><<<2 * num_sms(), 256, 0, st>>>(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout);
+  BD_CHECK_ARG(Cout <= 256, "bd_conv_in_wgrad: Cout <= 256");
+  conv_in_wgrad_kernel<36><<<2 * num_sms(), 256, (size_t)Cout * (Cin * 9 + 1) * sizeof(float), st>>>(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
@@ -705,7 +741,8 @@ int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const fl
     if (dbias) zero_f32_kernel<<<1, 256, 0, st>>>(dbias, Cout);
     count_launch(2);
   }
-  conv_out_wgrad_kernel<36><<<2 * num_sms(), 128, 0, st>>>((const __half*)x, ld_x, dy_nchw, dw, dbias, B, Cin, H, W, Cout);
+  BD_CHECK_ARG(Cin % 4 == 0 && Cin / 4 <= 256 && 256 % (Cin / 4) == 0, "bd_conv_out_bwd: Cin/4 must divide 256");
+  conv_out_wgrad_kernel<36><<<2 * num_sms(), 256, ((size_t)9 * Cout * Cin + 4) * sizeof(float), st>>>((const __half*)x, ld_x, dy_nchw, dw, dbias, B, Cin, H, W, Cout);
   count_launch(2);
   BD_CHECK_LAUNCH();
   return BD_OK;
