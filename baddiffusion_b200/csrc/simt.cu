@@ -395,43 +395,55 @@ __global__ void __launch_bounds__(256) conv_in_fwd_kernel(const float* __restric
   }
 }
 
-// conv_in wgrad: dW[tap][co][ci] += sum_p dY[p][co] x[ci][src(p,tap)].  thread = (co, pixel lane); the Cin*9 (<= 36)
-// input taps of a pixel are warp-uniform broadcast loads; block partials meet in shared memory, then one global atomic
-// per output and block.
+// conv_in wgrad: dW[tap][co][ci] += sum_p dY[p][co] x[ci][src(p,tap)].  Pixels are processed in chunks of 64 whose
+// Cin*9 (<= 36) input taps are staged in shared memory once; thread = (co, pixel lane) reads dY coalesced and the taps
+// as shared-memory broadcasts.  Block partials meet in shared memory, then one global atomic per output and block.
 template <int KMAX>
 __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const __half* __restrict__ dy,
                                                             int64_t lddy, float* __restrict__ dw,
                                                             float* __restrict__ dbias, int B, int Cin, int H, int W,
                                                             int Cout) {
-  extern __shared__ float sacc[];  // [Cout][K] + bias[Cout]
+  extern __shared__ float sacc[];  // [Cout][K+1] | patches [64][KMAX]
   const int K = Cin * 9;
+  float* sx = sacc + Cout * (K + 1);
   for (int i = threadIdx.x; i < Cout * (K + 1); i += blockDim.x) sacc[i] = 0.f;
-  __syncthreads();
   const int64_t P = (int64_t)B * H * W;
   const int64_t chunk = (P + gridDim.x - 1) / gridDim.x;
   const int64_t p0 = blockIdx.x * chunk, p1 = p0 + chunk < P ? p0 + chunk : P;
   const int lanes_p = blockDim.x / Cout > 0 ? blockDim.x / Cout : 1;
   const int co = threadIdx.x % Cout, pl = threadIdx.x / Cout;
-  if (pl < lanes_p && threadIdx.x < lanes_p * Cout) {
-    float acc[KMAX], bacc = 0.f;
+  const bool active = pl < lanes_p;
+  float acc[KMAX], bacc = 0.f;
 #pragma unroll
-    for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
-    for (int64_t p = p0 + pl; p < p1; p += lanes_p) {
-      const int ww = (int)(p % W);
-      const int64_t q = p / W;
-      const int hh = (int)(q % H), b = (int)(q / H);
-      const float d = __half2float(dy[p * lddy + co]);
-      bacc += d;
+  for (int k = 0; k < KMAX; ++k) acc[k] = 0.f;
+  for (int64_t pc = p0; pc < p1; pc += 64) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < 64 * K; i += blockDim.x) {
+      const int pix = i / K, k = i % K;
+      const int64_t p = pc + pix;
+      float xv = 0.f;
+      if (p < p1) {
+        const int ww = (int)(p % W);
+        const int64_t q = p / W;
+        const int hh = (int)(q % H), b = (int)(q / H);
+        const int ci = k / 9, tap = k % 9;
+        const int sh = hh + tap / 3 - 1, sxx = ww + tap % 3 - 1;
+        if (sh >= 0 && sh < H && sxx >= 0 && sxx < W) xv = x[(((int64_t)b * Cin + ci) * H + sh) * W + sxx];
+      }
+      sx[pix * KMAX + k] = xv;
+    }
+    __syncthreads();
+    if (active) {
+      for (int pix = pl; pix < 64 && pc + pix < p1; pix += lanes_p) {
+        const float d = __half2float(dy[(pc + pix) * lddy + co]);
+        bacc += d;
 #pragma unroll
-      for (int k = 0; k < KMAX; ++k) {
-        if (k < K) {
-          const int ci = k / 9, tap = k % 9;
-          const int sh = hh + tap / 3 - 1, sx = ww + tap % 3 - 1;
-          const float xv = (sh >= 0 && sh < H && sx >= 0 && sx < W) ? __ldg(x + (((int64_t)b * Cin + ci) * H + sh) * W + sx) : 0.f;
-          acc[k] = fmaf(d, xv, acc[k]);
-        }
+        for (int k = 0; k < KMAX; ++k)
+          if (k < K) acc[k] = fmaf(d, sx[pix * KMAX + k], acc[k]);
       }
     }
+  }
+  if (active) {
 #pragma unroll
     for (int k = 0; k < KMAX; ++k)
       if (k < K) atomicAdd(&sacc[co * (K + 1) + k], acc[k]);
@@ -707,7 +719,7 @@ int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* 
     count_launch(2);
   }
   BD_CHECK_ARG(Cout <= 256, "bd_conv_in_wgrad: Cout <= 256");
-  conv_in_wgrad_kernel<36><<<2 * num_sms(), 256, (size_t)Cout * (Cin * 9 + 1) * sizeof(float), st>>>(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout);
+  conv_in_wgrad_kernel<36><<<2 * num_sms(), 256, ((size_t)Cout * (Cin * 9 + 1) + 64 * 36) * sizeof(float), st>>>(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
