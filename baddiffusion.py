@@ -115,7 +115,8 @@ class TrainingConfig:  # baddiffusion.py:84-128
 
 def naming_fn(config):  # baddiffusion.py:130-134
     add_on = f"_{config.postfix}" if config.postfix else ""
-    return f"res_{config.ckpt}_{config.dataset}_ep{config.epoch}_c{config.clean_rate}_p{config.poison_rate}_{config.trigger}-{config.target}{add_on}"
+    ck = os.path.basename(os.path.normpath(str(config.ckpt)))  # local checkpoint directories: name the run after the id
+    return f"res_{ck}_{config.dataset}_ep{config.epoch}_c{config.clean_rate}_p{config.poison_rate}_{config.trigger}-{config.target}{add_on}"
 
 
 def setup(args):
