@@ -248,31 +248,36 @@ __global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------
+__global__ void zero_f32_kernel(float* p, size_t n);
+
 // small generic fp32 GEMM (strided): C[m,n] (+)= sum_k act(A[m,k]) * B[k,n] + bias[n]
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A, int64_t sam, int64_t sak,
                                                     const float* __restrict__ Bm, int64_t sbk, int64_t sbn,
                                                     float* __restrict__ C, int64_t scm, int64_t scn,
                                                     const float* __restrict__ bias, int M, int N, int K,
-                                                    int accumulate, int act_silu_a) {
+                                                    int accumulate, int act_silu_a, int ksplit) {
   __shared__ float As[TK][LDS];
   __shared__ float Bs[TK][LDS];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
+  // split-K: slice blockIdx.z of the reduction; partial results meet through atomics (C zeroed by the host)
+  const int kper = ((K + ksplit - 1) / ksplit + TK - 1) / TK * TK;
+  const int kbeg = blockIdx.z * kper, kend = min(K, kbeg + kper);
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += TK) {
+  for (int k0 = kbeg; k0 < kend; k0 += TK) {
     for (int i = tid; i < TK * TM; i += 256) {
       int kk = i % TK, mm = i / TK;  // consecutive threads -> consecutive k (fast when sak == 1)
       int m = m0 + mm, k = k0 + kk;
-      float v = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f;
+      float v = (m < M && k < kend) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.f;
       if (act_silu_a == 1) v = silu_f(v);
       As[kk][mm] = v;
       int nn = i / TK, n = n0 + nn;
-      float bv = (n < N && k < K) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
+      float bv = (n < N && k < kend) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.f;
       if (act_silu_a == 2) bv = silu_f(bv);
       Bs[kk][nn] = bv;
     }
@@ -297,9 +302,10 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
       if (n >= N) continue;
-      float v = acc[i][j] + (bias ? bias[n] : 0.f);
+      float v = acc[i][j] + ((bias && blockIdx.z == 0) ? bias[n] : 0.f);
       float* c = C + (int64_t)m * scm + (int64_t)n * scn;
-      *c = accumulate ? (*c + v) : v;
+      if (ksplit > 1) atomicAdd(c, v);
+      else *c = accumulate ? (*c + v) : v;
     }
   }
 }
@@ -658,8 +664,19 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
              int64_t scm, int64_t scn, const float* bias, int M, int N, int K, int accumulate, int act_silu_a,
              void* stream) {
   BD_CHECK_ARG(A && Bm && C && M > 0 && N > 0 && K > 0, "bd_sgemm: bad argument");
-  sgemm_kernel<<<dim3(ceil_div(M, TM), ceil_div(N, TN)), 256, 0, (cudaStream_t)stream>>>(
-      A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias, M, N, K, accumulate, act_silu_a);
+  const int gx = ceil_div(M, TM), gy = ceil_div(N, TN);
+  int ksplit = 1;
+  if (gx * gy < num_sms() && K >= 512 && scn == 1 && scm == N) {  // few tiles, long reduction, dense C
+    ksplit = ceil_div(2 * num_sms(), gx * gy);
+    if (ksplit > K / 128) ksplit = K / 128;
+    if (ksplit < 1) ksplit = 1;
+  }
+  if (ksplit > 1 && !accumulate) {
+    zero_f32_kernel<<<ceil_div((size_t)M * N, 2048), 256, 0, (cudaStream_t)stream>>>(C, (size_t)M * N);
+    count_launch(1);
+  }
+  sgemm_kernel<<<dim3(gx, gy, ksplit), 256, 0, (cudaStream_t)stream>>>(
+      A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias, M, N, K, accumulate, act_silu_a, ksplit);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

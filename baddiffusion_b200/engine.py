@@ -288,7 +288,8 @@ class UNetEngine:
                 ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True)
                 # temb projection: per-sample column sums (resnet.py:577-580 broadcast add)
                 ops.colsum_f16(d_h1.view(B, H * H, Cout), dcol, H * H, B, accumulate=True)
-                ops.conv_wgrad(a1, d_h1, g["conv1.weight"], g["conv1.bias"], ksize=3, accumulate=True, impl=impl)
+                # d(conv1.bias) == d(time_emb_proj.bias): both are the column sums above, added once in _emit_temb_bwd
+                ops.conv_wgrad(a1, d_h1, g["conv1.weight"], None, ksize=3, accumulate=True, impl=impl)
                 ops.conv_dgrad(d_h1, w1, d_a1, ksize=3, impl=impl)
                 # input gradient: residual / shortcut branch + norm1 branch (+ whatever is already there)
                 if has_sc:
@@ -474,6 +475,7 @@ class UNetEngine:
         wtp32 = self.flat32[lay.tproj_w_offset: lay.tproj_w_offset + ncol * temb_dim].view(ncol, temb_dim)
         g_wtp = self.gflat[lay.tproj_w_offset: lay.tproj_w_offset + ncol * temb_dim].view(ncol, temb_dim)
         g_btp = self.gflat[lay.tproj_b_offset: lay.tproj_b_offset + ncol]
+        g_c1b = self.gflat[lay.conv1_b_offset: lay.conv1_b_offset + ncol]  # all conv1.bias, same column order
         w2 = self.P32("time_embedding.linear_2.weight")
         g_w1, g_b1 = self.G32("time_embedding.linear_1.weight"), self.G32("time_embedding.linear_1.bias")
         g_w2, g_b2 = self.G32("time_embedding.linear_2.weight"), self.G32("time_embedding.linear_2.bias")
@@ -488,6 +490,7 @@ class UNetEngine:
             # time_emb_proj: y = silu(emb) @ Wtp^T + b
             ops.sgemm(dt, 1, ncol, self.emb, temb_dim, 1, g_wtp, temb_dim, 1, ncol, temb_dim, B, accumulate=True, act=2)
             ops.sgemm(ones, 0, 1, dt, ncol, 1, g_btp, 0, 1, 1, ncol, B, accumulate=True)
+            ops.sgemm(ones, 0, 1, dt, ncol, 1, g_c1b, 0, 1, 1, ncol, B, accumulate=True)
             ops.sgemm(dt, ncol, 1, wtp32, temb_dim, 1, d_se, temb_dim, 1, B, temb_dim, ncol)
             ops.silu_bwd_f32(d_se, self.emb, d_emb)
             # linear_2: emb = silu(h1) @ W2^T + b2

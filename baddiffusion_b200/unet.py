@@ -138,7 +138,8 @@ class FlatLayout:
         names = list(self.entries)
         tproj_w = [p + "time_emb_proj.weight" for p in resnet_prefixes(cfg)]
         tproj_b = [p + "time_emb_proj.bias" for p in resnet_prefixes(cfg)]
-        special = set(tproj_w) | set(tproj_b)
+        conv1_b = [p + "conv1.bias" for p in resnet_prefixes(cfg)]  # same column order: d(conv1.bias) == d(time_emb_proj.bias)
+        special = set(tproj_w) | set(tproj_b) | set(conv1_b)
         for k in names:
             if k in special:
                 continue
@@ -166,6 +167,10 @@ class FlatLayout:
         self.n_gemm = off  # end of region A
         self.tproj_b_offset = off
         for k in tproj_b:
+            place(k, align=False)
+        off = (off + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.conv1_b_offset = off
+        for k in conv1_b:
             place(k, align=False)
         for k in order_b:
             # q/k/v biases adjacent (3C contiguous): do not pad between them

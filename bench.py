@@ -254,7 +254,7 @@ def run_ours(args):
         k_ms = tot / reps
         flops = 2.0 * B * H * H * C * C * 9
         achieved = flops / (k_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "umma_fprop_kernel<128> conv3x3 128->128 @32x32, B=128",
+        roof = {"bound": "tensor", "kernel": "umma_conv3t_kernel (3x3 conv, halo reuse) 128->128 @32x32, B=128",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                 "traffic": None, "peak_source": f"{pk['src']} (burst, kernel timed alone)", "ms_per_launch": k_ms,
                 "algorithmic_flops_per_launch": flops,
