@@ -89,7 +89,7 @@ struct Smem {
 // fprop-style kernel
 // =============================================================================================
 template <int BN, int kStages, bool B_MN>
-__global__ void __launch_bounds__(320, 1) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                             const __grid_constant__ CUtensorMap tmA1,
                                                             const __grid_constant__ CUtensorMap tmB0,
                                                             const __grid_constant__ CUtensorMap tmB1,
@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(320, 1) umma_fprop_kernel(const __grid_constan
 // wgrad-style kernel: both operands MN-major, K = pixels.  grid (m_tiles*n_tiles, z, splits)
 // =============================================================================================
 template <int BN, int kStages>
-__global__ void __launch_bounds__(192, 1) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
+__global__ void __launch_bounds__(192, 2) umma_wgrad_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmB,
                                                             const WgradParams p) {
   using L = Smem<BN, kStages>;
@@ -412,7 +412,7 @@ static bool pick_box(int H, int W, int pixels, int* bw, int* bh, int* bn) {
 template <int BN, bool B_MN>
 static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
                           const FpropParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int kStages = BN == 128 ? 5 : 6;
+  constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one drains its accumulator while the other streams operands
   using L = Smem<BN, kStages>;
   auto kern = umma_fprop_kernel<BN, kStages, B_MN>;
   static bool attr_set = false;
@@ -575,7 +575,7 @@ int wgrad_supported(const WgradCall& c) {
 
 template <int BN>
 static int launch_wgrad_t(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int kStages = BN == 128 ? 5 : 6;
+  constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one drains its accumulator while the other streams operands
   using L = Smem<BN, kStages>;
   auto kern = umma_wgrad_kernel<BN, kStages>;
   static bool attr_set = false;
