@@ -12,8 +12,11 @@ namespace bd {
 constexpr int kGnMaxSplits = 32;
 constexpr int UNR = 4;
 
-static inline int gn_splits(int B, int HW, int rows) {
-  int want = ceil_div(4 * num_sms(), B > 0 ? B : 1);
+// Splits per sample: B * splits blocks must ALL be resident at once (`per_sm` blocks fit on an SM) -- these kernels are
+// bandwidth bound, so an uneven spread over the SMs costs nothing, but a second, nearly empty wave costs a whole pass.
+static inline int gn_splits(int B, int HW, int rows, int per_sm) {
+  int want = per_sm * num_sms() / (B > 0 ? B : 1);
+  if (want < 1) want = 1;
   int cap = HW / (rows * UNR) > 0 ? HW / (rows * UNR) : 1;
   int s = want < cap ? want : cap;
   if (s > kGnMaxSplits) s = kGnMaxSplits;
@@ -21,7 +24,7 @@ static inline int gn_splits(int B, int HW, int rows) {
 }
 
 // smem: red[rows][C][2]
-__global__ void gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float* __restrict__ work, int HW, int C,
+__global__ void __launch_bounds__(256, 4) gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float* __restrict__ work, int HW, int C,
                                 int G, int splits) {
   extern __shared__ float red[];
   const int C8 = C / 8, rows = blockDim.x / C8;
@@ -291,13 +294,13 @@ size_t bd_gn_workspace_floats(int B, int C) {
   return (size_t)(B > 0 ? B : 1) * (kGnMaxSplits * 2 * (size_t)C + 2 * (size_t)C);
 }
 
-static inline void gn_geometry(int B, int HW, int C, int* threads, int* rows, int* splits, int* asplits) {
+static inline void gn_geometry(int B, int HW, int C, int per_sm, int* threads, int* rows, int* splits, int* asplits) {
   const int C8 = C / 8;
   *rows = C8 >= 256 ? 1 : 256 / C8;
   *threads = C8 * (*rows);
-  *splits = gn_splits(B, HW, *rows);
-  // the apply passes have no reduction: give them ~8 blocks per SM
-  int want = ceil_div(4 * num_sms(), B);
+  *splits = gn_splits(B, HW, *rows, per_sm);
+  int want = per_sm * num_sms() / B;
+  if (want < 1) want = 1;
   int cap = HW / (*rows) > 0 ? HW / (*rows) : 1;
   *asplits = want < cap ? want : cap;
   if (*asplits < 1) *asplits = 1;
@@ -310,7 +313,7 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
                "bd_groupnorm_fwd: need C %% 8 == 0, C %% G == 0, ld %% 8 == 0, C <= 2048 (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
   int threads, rows, splits, asplits;
-  gn_geometry(B, HW, C, &threads, &rows, &splits, &asplits);
+  gn_geometry(B, HW, C, 4, &threads, &rows, &splits, &asplits);
   gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, work, HW, C, G, splits);
   // stats may be omitted by inference callers: park them behind the partials
@@ -332,7 +335,7 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
                "bd_groupnorm_bwd: bad shape (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
   int threads, rows, splits, asplits;
-  gn_geometry(B, HW, C, &threads, &rows, &splits, &asplits);
+  gn_geometry(B, HW, C, 3, &threads, &rows, &splits, &asplits);
   gn_bwd_reduce_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu);
   // group sums live right behind the per-split partials in the workspace

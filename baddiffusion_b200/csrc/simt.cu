@@ -600,6 +600,18 @@ __global__ void zero_f32_kernel(float* p, size_t n) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = 0.f;
 }
 
+// fast paths for the UNet's own shapes (convio.cu)
+bool conv_in_fwd_fast(const float* x, const float* w, const float* bias, __half* y, int64_t ldy, int B, int Cin, int H,
+                      int W, int Cout, cudaStream_t st);
+bool conv_out_dgrad_fast(const float* w, const float* dy, __half* dx, int64_t lddx, int B, int Cin, int H, int W, int Cout,
+                         cudaStream_t st);
+bool conv_out_fwd_fast(const __half* x, int64_t ldx, const float* w, const float* bias, float* y, int B, int Cin, int H,
+                       int W, int Cout, cudaStream_t st);
+bool conv_out_wgrad_fast(const __half* x, int64_t ldx, const float* dy, float* dw, float* dbias, int B, int Cin, int H,
+                         int W, int Cout, cudaStream_t st);
+bool conv_in_wgrad_fast(const float* x, const __half* dy, int64_t lddy, float* dw, float* dbias, int B, int Cin, int H,
+                        int W, int Cout, cudaStream_t st);
+
 // exported to api.cu ---------------------------------------------------------------------------
 int simt_conv_launch(const bd_conv_args* a, bool dgrad, cudaStream_t st) {
   ConvGeom g;
@@ -714,6 +726,11 @@ int bd_colsum_f16(const void* x, int64_t ld_x, float* out, int64_t ld_out, int B
 int bd_conv_in_fwd(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, int B, int Cin,
                    int H, int W, int Cout, void* stream) {
   BD_CHECK_ARG(x_nchw && w_packed && y && Cin > 0 && Cin <= 4 && Cout % 8 == 0 && ld_y % 8 == 0, "bd_conv_in_fwd: need Cin <= 4, Cout %% 8 == 0");
+  if (getenv("BD_NO_CONVIO") == nullptr &&
+      conv_in_fwd_fast(x_nchw, w_packed, bias, (__half*)y, ld_y, B, Cin, H, W, Cout, (cudaStream_t)stream)) {
+    BD_CHECK_LAUNCH();
+    return BD_OK;
+  }
   size_t smem = ((size_t)Cin * 9 * Cout + Cout) * sizeof(float);
   BD_CHECK_ARG(smem <= 200 * 1024, "bd_conv_in_fwd: Cout too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(conv_in_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -735,6 +752,11 @@ int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* 
     if (dbias) zero_f32_kernel<<<1, 256, 0, st>>>(dbias, Cout);
     count_launch(2);
   }
+  if (getenv("BD_NO_CONVIO") == nullptr &&
+      conv_in_wgrad_fast(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout, st)) {
+    BD_CHECK_LAUNCH();
+    return BD_OK;
+  }
   BD_CHECK_ARG(Cout <= 256, "bd_conv_in_wgrad: Cout <= 256");
   conv_in_wgrad_kernel<36><<<2 * num_sms(), 256, ((size_t)Cout * (Cin * 9 + 1) + 64 * 36) * sizeof(float), st>>>(x_nchw, (const __half*)dy, ld_dy, dw, dbias, B, Cin, H, W, Cout);
   count_launch(1);
@@ -745,6 +767,11 @@ int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* 
 int bd_conv_out_fwd(const void* x, int64_t ld_x, const float* w_packed, const float* bias, float* y_nchw, int B, int Cin,
                     int H, int W, int Cout, void* stream) {
   BD_CHECK_ARG(x && w_packed && y_nchw && Cout > 0 && Cout <= 4 && Cin % 4 == 0 && ld_x % 4 == 0, "bd_conv_out_fwd: need Cout <= 4, Cin %% 4 == 0");
+  if (getenv("BD_NO_CONVIO") == nullptr &&
+      conv_out_fwd_fast((const __half*)x, ld_x, w_packed, bias, y_nchw, B, Cin, H, W, Cout, (cudaStream_t)stream)) {
+    BD_CHECK_LAUNCH();
+    return BD_OK;
+  }
   size_t smem = (size_t)Cout * Cin * 9 * sizeof(float);
   BD_CHECK_ARG(smem <= 200 * 1024, "bd_conv_out_fwd: Cin too large");
   if (smem > 48 * 1024) cudaFuncSetAttribute(conv_out_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -764,15 +791,23 @@ int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const fl
   size_t total = (size_t)B * H * W * (Cin / 8);
   int grid = (int)((total + 255) / 256);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
-  conv_out_dgrad_kernel<<<grid, 256, smem, st>>>(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout);
+  const bool fast = getenv("BD_NO_CONVIO") == nullptr;
+  if (!(fast && conv_out_dgrad_fast(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout, st))) {
+    conv_out_dgrad_kernel<<<grid, 256, smem, st>>>(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout);
+    count_launch(1);
+  }
   if (!accumulate) {
     zero_f32_kernel<<<ceil_div((size_t)Cout * Cin * 9, 2048), 256, 0, st>>>(dw, (size_t)Cout * Cin * 9);
     if (dbias) zero_f32_kernel<<<1, 256, 0, st>>>(dbias, Cout);
     count_launch(2);
   }
+  if (fast && conv_out_wgrad_fast((const __half*)x, ld_x, dy_nchw, dw, dbias, B, Cin, H, W, Cout, st)) {
+    BD_CHECK_LAUNCH();
+    return BD_OK;
+  }
   BD_CHECK_ARG(Cin % 4 == 0 && Cin / 4 <= 256 && 256 % (Cin / 4) == 0, "bd_conv_out_bwd: Cin/4 must divide 256");
   conv_out_wgrad_kernel<36><<<2 * num_sms(), 256, ((size_t)9 * Cout * Cin + 4) * sizeof(float), st>>>((const __half*)x, ld_x, dy_nchw, dw, dbias, B, Cin, H, W, Cout);
-  count_launch(2);
+  count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }

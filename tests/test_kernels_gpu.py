@@ -316,8 +316,10 @@ def test_conv_stride2(ops, impl, pad, B, H, Cc):
     assert rel_err(db, dyr.sum((0, 2, 3))) < 2e-3
 
 
-def test_conv_in_out(ops):
-    B, H, Cc = 3, 32, 128
+@pytest.mark.parametrize("H,Cc", [(32, 128), (40, 128), (12, 64), (16, 256)])
+def test_conv_in_out(ops, H, Cc):
+    # (32|40, 128): the register-tiled kernels of convio.cu (40: ragged row segments); others: general kernels
+    B = 3
     torch.manual_seed(0)
     x = torch.randn(B, 3, H, H, device="cuda")
     w_in = torch.randn(Cc, 3, 3, 3, device="cuda") / 5
