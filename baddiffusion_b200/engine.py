@@ -12,6 +12,7 @@ The plan is static for a given (model config, batch, train) so it can be replaye
 from __future__ import annotations
 
 import math
+import os
 from typing import Callable, Dict, List, Optional
 
 import torch
@@ -63,6 +64,12 @@ class UNetEngine:
             raise NotImplementedError("training with mid_block_scale_factor != 1 is not implemented")
         maxC = max(max(cfg.block_out_channels) * 2, 64)
         self.gn_work = torch.empty(ops.gn_workspace_floats(batch, maxC), device=self.dev)
+        # Parameter gradients are off the critical path of backward (nothing downstream reads them before the
+        # optimizer): they run on a side stream, forked after the activation gradient they consume is ready and
+        # joined before the timestep-MLP backward.  The small layers (8x8, 4x4) fill a fraction of the SMs, so the
+        # two streams genuinely overlap; inside a CUDA graph the fork/join events become plain dependency edges.
+        self.side = (torch.cuda.Stream(device=self.dev)
+                     if train and not os.environ.get("BD_NO_SIDE_STREAM") else None)
         self._build()
 
     # ------------------------------------------------------------------ parameter views
@@ -99,6 +106,30 @@ class UNetEngine:
         if self.train:
             a.g = self.new(H, C)
         return a
+
+    # ------------------------------------------------------------------ side stream (parameter gradients)
+    def _fork(self, fn: Callable[[], None]):
+        """Run fn on the side stream once everything queued so far on the current stream is done.  Whatever fn reads
+        must not be rewritten on the main stream before `_join` (callers give such tensors per-layer storage)."""
+        if self.side is None:
+            fn()
+            return
+        ev = torch.cuda.Event()
+        ev.record()
+        self.side.wait_event(ev)
+        with torch.cuda.stream(self.side):
+            fn()
+
+    def _join(self):
+        if self.side is None:
+            return
+        ev = torch.cuda.Event()
+        ev.record(self.side)
+        torch.cuda.current_stream().wait_event(ev)
+
+    def grad_buf(self, H, C, tag):
+        """Activation gradient that a forked wgrad reads: per layer when the side stream is on, pooled otherwise."""
+        return self.new(H, C) if self.side is not None else self.scratch(H, C, tag)
 
     # ------------------------------------------------------------------ plan construction
     def _build(self):
@@ -272,24 +303,30 @@ class UNetEngine:
             gws = self.G32(p + "conv_shortcut.weight") if has_sc else None
             gbs = self.G32(p + "conv_shortcut.bias") if has_sc else None
             d_a2 = self.scratch(H, Cout, "da2")
-            d_h1 = self.scratch(H, Cout, "dh1")
+            d_h1 = self.grad_buf(H, Cout, "dh1")
             d_a1 = self.scratch(H, Cin, "da1")
             dcol = self.d_tproj[:, col: col + Cout]
             x_filled = x.g_filled
             dout = out.g
             B = self.B
 
-            def bw():
+            def wg2():
                 # conv2 (+ shortcut) parameter gradients
                 ops.conv_wgrad(a2, dout, g["conv2.weight"], g["conv2.bias"], ksize=3, accumulate=True, impl=impl)
                 if has_sc:
                     ops.conv_wgrad(x.t, dout, gws, gbs, ksize=1, accumulate=True, impl=impl)
-                ops.conv_dgrad(dout, w2, d_a2, ksize=3, impl=impl)
-                ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True)
+
+            def wg1():
                 # temb projection: per-sample column sums (resnet.py:577-580 broadcast add)
                 ops.colsum_f16(d_h1.view(B, H * H, Cout), dcol, H * H, B, accumulate=True)
                 # d(conv1.bias) == d(time_emb_proj.bias): both are the column sums above, added once in _emit_temb_bwd
                 ops.conv_wgrad(a1, d_h1, g["conv1.weight"], None, ksize=3, accumulate=True, impl=impl)
+
+            def bw():
+                self._fork(wg2)
+                ops.conv_dgrad(dout, w2, d_a2, ksize=3, impl=impl)
+                ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True)
+                self._fork(wg1)
                 ops.conv_dgrad(d_h1, w1, d_a1, ksize=3, impl=impl)
                 # input gradient: residual / shortcut branch + norm1 branch (+ whatever is already there)
                 if has_sc:
@@ -352,17 +389,17 @@ class UNetEngine:
             g_bqkv = self.gflat[boff: boff + 3 * C]
             g_wp, g_bp = self.G32(p + "proj_attn.weight").view(1, C, C), self.G32(p + "proj_attn.bias")
             d_ao = self.scratch(H, C, "dao")
-            d_qkv = self.scratch(H, 3 * C, "dqkv")
+            d_qkv = self.grad_buf(H, 3 * C, "dqkv")
             d_a = self.scratch(H, C, "daa")
             x_filled = x.g_filled
             dout = out.g
 
             def bw():
-                ops.conv_wgrad(ao, dout, g_wp, g_bp, ksize=1, accumulate=True, impl=impl)
+                self._fork(lambda: ops.conv_wgrad(ao, dout, g_wp, g_bp, ksize=1, accumulate=True, impl=impl))
                 ops.conv_dgrad(dout, wp, d_ao, ksize=1, impl=impl)
                 ops.attention_bwd(qkv.view(B, S, 3 * C), probs, d_ao.view(B, S, C), d_qkv.view(B, S, 3 * C), work, B, S, C,
                                   heads, sm_scale, impl=impl)
-                ops.conv_wgrad(a, d_qkv, g_wqkv, g_bqkv, ksize=1, accumulate=True, impl=impl)
+                self._fork(lambda: ops.conv_wgrad(a, d_qkv, g_wqkv, g_bqkv, ksize=1, accumulate=True, impl=impl))
                 ops.conv_dgrad(d_qkv, wqkv, d_a, ksize=1, impl=impl)
                 if x_filled:
                     ops.add_f16(x.g, dout, x.g)
@@ -392,7 +429,8 @@ class UNetEngine:
             dout = out.g
 
             def bw():
-                ops.conv_wgrad(x.t, dout, gw_, gb_, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad, accumulate=True)
+                self._fork(lambda: ops.conv_wgrad(x.t, dout, gw_, gb_, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad,
+                                                  accumulate=True))
                 ops.conv_dgrad(dout, w, x.g, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad, residual=x.g if x_filled else None)
 
             self.bwd.append(bw)
@@ -422,7 +460,7 @@ class UNetEngine:
             assert not x.g_filled
 
             def bw():
-                ops.conv_wgrad(u, dout, gw_, gb_, ksize=3, accumulate=True, impl=impl)
+                self._fork(lambda: ops.conv_wgrad(u, dout, gw_, gb_, ksize=3, accumulate=True, impl=impl))
                 ops.conv_dgrad(dout, w, d_u, ksize=3, impl=impl)
                 ops.upsample2x_bwd(d_u, x.g)
 
@@ -487,6 +525,7 @@ class UNetEngine:
         dt = self.d_tproj
 
         def bw():
+            self._join()  # the column sums in d_tproj (and every parameter gradient) come from the side stream
             # time_emb_proj: y = silu(emb) @ Wtp^T + b
             ops.sgemm(dt, 1, ncol, self.emb, temb_dim, 1, g_wtp, temb_dim, 1, ncol, temb_dim, B, accumulate=True, act=2)
             ops.sgemm(ones, 0, 1, dt, ncol, 1, g_btp, 0, 1, 1, ncol, B, accumulate=True)
@@ -516,6 +555,7 @@ class UNetEngine:
     def run_backward(self):
         for f in self.bwd:
             f()
+        self._join()
 
     def forward(self, x: torch.Tensor, timesteps: torch.Tensor) -> torch.Tensor:
         """x (B,C,S,S) fp32 NCHW, timesteps (B,) int64 -> eps_hat (B,C,S,S) fp32 (engine-owned buffer)."""
