@@ -54,13 +54,14 @@ _SIGS = {
     "bd_sgemm": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_gn_workspace_floats": (sz, [i32, i32]),
     "bd_groupnorm_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
-    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
+    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
     "bd_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_dgrad": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_wgrad": (i32, [vp, i64, vp, i64, vp, vp] + [i32] * 10 + [vp]),
     "bd_pack_conv_weight": (i32, [vp, vp, vp, i32, i32, i32, vp]),
     "bd_cast_f32_to_f16": (i32, [vp, vp, sz, vp]),
     "bd_colsum_f16": (i32, [vp, i64, vp, i64, i32, i64, i32, i32, vp]),
+    "bd_bias_from_gsum": (i32, [vp, i32, i32, i32, vp]),
     "bd_silu_bwd_f32": (i32, [vp, vp, vp, sz, vp]),
     "bd_silu_f32_to_f16": (i32, [vp, vp, sz, vp]),
     "bd_conv_in_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),

@@ -135,6 +135,7 @@ static int check_conv(const bd_conv_args* a, const char* who) {
 
 }  // namespace bd
 
+namespace bd { namespace umma { const __half* conv3_identity(); } }
 using namespace bd;
 
 extern "C" {
@@ -143,6 +144,7 @@ int bd_init(void) {
   int* f = umma::error_flag();
   if (!f) { set_error("bd_init: cudaMalloc failed"); return BD_ERR_CUDA; }
   (void)num_sms();
+  (void)umma::conv3_identity();
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) { set_error("bd_init: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
   return BD_OK;

@@ -7,10 +7,31 @@
 // consecutive 16-byte vectors of a pixel row (coalesced); pixels are strided by `rows` with 4 loads in flight.
 #include "common.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace bd {
 
 constexpr int kGnMaxSplits = 32;
 constexpr int UNR = 4;
+
+// SiLU and its derivative from ONE special-function op.  These kernels are bound by the 16-lane MUFU pipe, not by HBM:
+// exp + reciprocal is 2 MUFU ops per element (28 kcycles for a 128 x 32 x 32 x 128 tensor = the whole measured run
+// time of the apply pass); tanh.approx.f32 is one.  Callers pass h = z/2 (the 1/2 is folded into the per-channel
+// affine coefficients):  sigmoid(z) = (1 + tanh h)/2,  silu(z) = h + h*tanh h,
+// silu'(z) = s*(1 + z*(1-s)) = s + s*h*(1 - tanh h).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float silu_h(float h) { return fmaf(h, tanh_approx(h), h); }
+__device__ __forceinline__ float dsilu_h(float h) {
+  const float t = tanh_approx(h);
+  const float u = fmaf(-h, t, h);        // z*(1-s)
+  const float sg = fmaf(0.5f, t, 0.5f);  // s
+  return fmaf(sg, u, sg);
+}
 
 // Splits per sample: B * splits blocks must ALL be resident at once (`per_sm` blocks fit on an SM) -- these kernels are
 // bandwidth bound, so an uneven spread over the SMs costs nothing, but a second, nearly empty wave costs a whole pass.
@@ -101,6 +122,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restri
     const int ch = v * 8 + k, g = ch / cpg;
     a[k] = stats[((int64_t)b * G + g) * 2 + 1] * gamma[ch];
     c[k] = beta[ch] - stats[((int64_t)b * G + g) * 2 + 0] * a[k];
+    if (apply_silu) { a[k] *= 0.5f; c[k] *= 0.5f; }   // h = z/2 for silu_h
   }
   const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
@@ -118,17 +140,13 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restri
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float z = fmaf(f[k], a[k], c[k]);
-          f[k] = apply_silu ? silu_f(z) : z;
+          f[k] = apply_silu ? silu_h(z) : z;
         }
         *reinterpret_cast<half8*>(yb + (int64_t)(p + u * rows) * ldy) = pack8(f);
       }
   }
 }
 
-__device__ __forceinline__ float dsilu(float z) {
-  float sg = __fdividef(1.0f, 1.0f + __expf(-z));
-  return sg * (1.0f + z * (1.0f - sg));
-}
 
 // backward pass 1: per (b, split, c): s1 = sum dz, s2 = sum dz * xhat    (dz = dy * silu'(z))
 // In the loop only  z = x*a + c  (a = rstd*gamma, c = beta - mean*a) is formed; sum dz*xhat is recovered from
@@ -147,8 +165,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
   for (int k = 0; k < 8; ++k) {
     const int ch = v * 8 + k, g = ch / cpg;
     const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
-    a[k] = rstd * gamma[ch];
-    c[k] = beta[ch] - mean * a[k];
+    a[k] = 0.5f * rstd * gamma[ch];            // h = z/2 for dsilu_h
+    c[k] = 0.5f * (beta[ch] - mean * rstd * gamma[ch]);
   }
   float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
@@ -168,7 +186,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       float dz = fd[k];
-      if (apply_silu) dz *= dsilu(fmaf(fx[k], a[k], c[k]));
+      if (apply_silu) dz *= dsilu_h(fmaf(fx[k], a[k], c[k]));
       s1[k] += dz;
       s2[k] = fmaf(dz, fx[k], s2[k]);
     }
@@ -178,7 +196,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float dz = fd[k];
-        if (apply_silu) dz *= dsilu(fmaf(fx[k], a[k], c[k]));
+        if (apply_silu) dz *= dsilu_h(fmaf(fx[k], a[k], c[k]));
         s1[k] += dz;
         s2[k] = fmaf(dz, fx[k], s2[k]);
       }
@@ -254,7 +272,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
     const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
     const float gA = gab[((int64_t)b * G + g) * 2 + 0], gB = gab[((int64_t)b * G + g) * 2 + 1];
     k1[k] = rstd * gamma[ch];
-    cz[k] = beta[ch] - mean * k1[k];
+    cz[k] = 0.5f * (beta[ch] - mean * k1[k]);  // h = z/2 = x*(k1/2) + cz for dsilu_h
     c1[k] = -rstd * rstd * gB;
     c0[k] = rstd * (mean * rstd * gB - gA);
   }
@@ -273,7 +291,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float dz = fd[k];
-        if (apply_silu) dz *= dsilu(fmaf(fx[k], k1[k], cz[k]));
+        if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
         float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
         if (add) o += fa[k];
         fx[k] = o;
@@ -283,9 +301,396 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
   }
 }
 
+
+// =============================================================================================================
+// Single-launch GroupNorm: ONE thread-block cluster per sample.  Each CTA of the cluster owns a pixel range; a thread
+// keeps up to VMAX of its 16-byte vectors in registers between the statistics pass and the apply pass (what does
+// not fit is re-read -- it was touched microseconds ago and is L2-resident), the per-CTA partial sums meet through
+// distributed shared memory in a fixed order (bitwise reproducible), and every CTA normalises its own range.
+// Against the three-kernel path above this is 1 launch instead of 3 and 4 B/element instead of 6 (forward),
+// 6-8 instead of 10-12 (backward).
+// =============================================================================================================
+constexpr int GN_VMAX = 4;   // default register-cache depth (vectors per thread); 8 is also compiled (BD_GN_VMAX)
+
+// Block-level reduction of per-thread, per-channel partials (thread (r, v) holds NV values for each of its 8 channels)
+// to per-channel sums chs[j][C] (fp32), bank-conflict free in both directions:
+//   red[((j*8 + k) * rows + r) * C8 + v]  -- consecutive lanes are consecutive v (and r): stride-1 stores;
+//   the summing thread takes (j, k, v) with v fastest: stride-1 loads, `rows` (<= 64) serial adds in 4 chains.
+template <int NV>
+__device__ __forceinline__ void gn_block_channel_sums(float* red, float* chs, const float (*vals)[8], int rows, int C8,
+                                                      int C, int r, int v) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[((j * 8 + k) * rows + r) * C8 + v] = vals[j][k];
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NV * C; idx += blockDim.x) {
+    const int j = idx / C, rem = idx - j * C, k = rem / C8, vv = rem - k * C8;
+    const float* src = red + (size_t)((j * 8 + k) * rows) * C8 + vv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int rr = 0;
+    for (; rr + 4 <= rows; rr += 4) {
+      a0 += src[(rr + 0) * C8];
+      a1 += src[(rr + 1) * C8];
+      a2 += src[(rr + 2) * C8];
+      a3 += src[(rr + 3) * C8];
+    }
+    for (; rr < rows; ++rr) a0 += src[rr * C8];
+    chs[j * C + vv * 8 + k] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+}
+
+// dynamic smem: red[threads][16] f32 | chs[2][C] f32 | grp[G][2] f64 | mr[G][2] f32
+template <int VMAX>
+__global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __restrict__ x, int64_t ldx,
+                                                              __half* __restrict__ y, int64_t ldy,
+                                                              const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, float* __restrict__ stats_out,
+                                                              int HW, int C, int G, float eps, int apply_silu) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  extern __shared__ __align__(16) unsigned char gsm[];
+  float* red = reinterpret_cast<float*>(gsm);
+  float* chs = red + (size_t)blockDim.x * 16;
+  double* grp = reinterpret_cast<double*>(chs + 2 * C);
+  float* mr = reinterpret_cast<float*>(grp + 2 * G);
+  const int C8 = C / 8, rows = blockDim.x / C8, cpg = C / G;
+  const int tid = threadIdx.x, v = tid % C8, r = tid / C8;
+  const int b = blockIdx.y;
+  const int p0 = (int)((int64_t)HW * rank / CS), p1 = (int)((int64_t)HW * (rank + 1) / CS);
+  const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
+  __half* yb = y + (int64_t)b * HW * ldy + v * 8;
+  half8 hv[VMAX];
+  float sq[2][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sq[0][k] = sq[1][k] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int p = p0 + r + i * rows;
+    if (p < p1) hv[i] = *reinterpret_cast<const half8*>(xb + (int64_t)p * ldx);
+  }
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int p = p0 + r + i * rows;
+    if (p < p1) {
+      float f[8];
+      unpack8(hv[i], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { sq[0][k] += f[k]; sq[1][k] = fmaf(f[k], f[k], sq[1][k]); }
+    }
+  }
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {  // what the register cache does not hold
+    float f[8];
+    unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sq[0][k] += f[k]; sq[1][k] = fmaf(f[k], f[k], sq[1][k]); }
+  }
+  gn_block_channel_sums<2>(red, chs, sq, rows, C8, C, r, v);
+  // per-channel affine parameters: issued now so their latency hides behind the cluster exchange
+  float ga[8], be[8];
+  {
+    const float4 g0 = *reinterpret_cast<const float4*>(gamma + v * 8), g1 = *reinterpret_cast<const float4*>(gamma + v * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(beta + v * 8), b1 = *reinterpret_cast<const float4*>(beta + v * 8 + 4);
+    ga[0] = g0.x; ga[1] = g0.y; ga[2] = g0.z; ga[3] = g0.w; ga[4] = g1.x; ga[5] = g1.y; ga[6] = g1.z; ga[7] = g1.w;
+    be[0] = b0.x; be[1] = b0.y; be[2] = b0.z; be[3] = b0.w; be[4] = b1.x; be[5] = b1.y; be[6] = b1.z; be[7] = b1.w;
+  }
+  for (int g = tid; g < G; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { ds += (double)chs[c]; dq += (double)chs[C + c]; }
+    grp[2 * g] = ds;
+    grp[2 * g + 1] = dq;
+  }
+  cl.sync();
+  // gather every peer's group partials with ONE remote (DSMEM) load per thread, then reduce locally in rank order:
+  // a single round trip instead of CS dependent ones
+  double* rgrp = reinterpret_cast<double*>(red);   // red[] is free again: [CS][2G] doubles
+  for (int i = tid; i < CS * 2 * G; i += blockDim.x) {
+    const int rk = i / (2 * G), j = i - rk * 2 * G;
+    rgrp[i] = cl.map_shared_rank(grp, rk)[j];
+  }
+  cl.barrier_arrive();  // this CTA no longer reads its peers' shared memory
+  __syncthreads();
+  for (int g = tid; g < G; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int rk = 0; rk < CS; ++rk) { ds += rgrp[rk * 2 * G + 2 * g]; dq += rgrp[rk * 2 * G + 2 * g + 1]; }
+    const double n = (double)HW * cpg;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float fm = (float)mean, fr = (float)(1.0 / sqrt(var + (double)eps));
+    mr[2 * g] = fm;
+    mr[2 * g + 1] = fr;
+    if (rank == 0 && stats_out) {
+      stats_out[((int64_t)b * G + g) * 2 + 0] = fm;
+      stats_out[((int64_t)b * G + g) * 2 + 1] = fr;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int g = (v * 8 + k) / cpg;
+    ga[k] *= mr[2 * g + 1];
+    be[k] -= mr[2 * g] * ga[k];
+    if (apply_silu) { ga[k] *= 0.5f; be[k] *= 0.5f; }   // h = z/2 for silu_h
+  }
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int p = p0 + r + i * rows;
+    if (p < p1) {
+      float f[8];
+      unpack8(hv[i], f);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float z = fmaf(f[k], ga[k], be[k]);
+        f[k] = apply_silu ? silu_h(z) : z;
+      }
+      *reinterpret_cast<half8*>(yb + (int64_t)p * ldy) = pack8(f);
+    }
+  }
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
+    float f[8];
+    unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float z = fmaf(f[k], ga[k], be[k]);
+      f[k] = apply_silu ? silu_h(z) : z;
+    }
+    *reinterpret_cast<half8*>(yb + (int64_t)p * ldy) = pack8(f);
+  }
+  cl.barrier_wait();  // peers may still be reading grp[]: do not retire before they are done
+}
+
+// Backward in one launch.  Phase 1: per-channel s1 = sum dz, s2 = sum dz*x over the CTA's pixels -> cluster-wide
+// totals (every CTA sums all peers' partials, fixed order) -> dgamma/dbeta (atomics, rank 0) and the per-group
+// gA, gB.  Phase 2: dx = k1*dz + c1*x + c0 (+ add).  Optionally the per-(sample, channel) sums of dx are produced
+// (gsum): they are the bias gradients of the convolution that made x and, for norm2, the time_emb_proj gradient
+// (D/models/resnet.py:574-580), which otherwise cost one extra pass over dx each.
+// dynamic smem: red[threads][16] f32 | chs[2][C] f32 | chs2[C] f32 | tot[2][C] f32 | gab[G][2] f32
+template <int VMAX>
+__global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
+    const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
+    const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gsum, int64_t ld_gsum, int HW, int C,
+    int G, int apply_silu) {
+  cg::cluster_group cl = cg::this_cluster();
+  const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  extern __shared__ __align__(16) unsigned char gsm[];
+  float* red = reinterpret_cast<float*>(gsm);
+  float* chs = red + (size_t)blockDim.x * 16;
+  float* chs2 = chs + 2 * C;
+  float* tot = chs2 + C;
+  float* gab = tot + 2 * C;
+  const int C8 = C / 8, rows = blockDim.x / C8, cpg = C / G;
+  const int tid = threadIdx.x, v = tid % C8, r = tid / C8;
+  const int b = blockIdx.y;
+  const int p0 = (int)((int64_t)HW * rank / CS), p1 = (int)((int64_t)HW * (rank + 1) / CS);
+  const int64_t rb = (int64_t)b * HW;
+  const __half* xb = x + rb * ldx + v * 8;
+  const __half* db = dy + rb * lddy + v * 8;
+  half8 hx[VMAX], hd[VMAX];
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int p = p0 + r + i * rows;
+    if (p < p1) {
+      hx[i] = *reinterpret_cast<const half8*>(xb + (int64_t)p * ldx);
+      hd[i] = *reinterpret_cast<const half8*>(db + (int64_t)p * lddy);
+    }
+  }
+  float k1[8], cz[8];   // k1 = rstd*gamma ; z/2 = x*(k1/2) + cz
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k, g = ch / cpg;
+    k1[k] = stats[((int64_t)b * G + g) * 2 + 1] * gamma[ch];
+    cz[k] = 0.5f * (beta[ch] - stats[((int64_t)b * G + g) * 2 + 0] * k1[k]);   // h = z/2 = x*(k1/2) + cz
+  }
+  {
+    float ss[2][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss[0][k] = ss[1][k] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VMAX; ++i) {
+      const int p = p0 + r + i * rows;
+      if (p < p1) {
+        float fx[8], fd[8];
+        unpack8(hx[i], fx);
+        unpack8(hd[i], fd);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float dz = fd[k];
+          if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+          fd[k] = dz;
+          ss[0][k] += dz;
+          ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
+        }
+        hd[i] = pack8(fd);   // keep dz, not dy: phase 2 does not evaluate silu' again
+      }
+    }
+    for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
+      float fx[8], fd[8];
+      unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), fx);
+      unpack8(*reinterpret_cast<const half8*>(db + (int64_t)p * lddy), fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz = fd[k];
+        if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+        ss[0][k] += dz;
+        ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
+      }
+    }
+    gn_block_channel_sums<2>(red, chs, ss, rows, C8, C, r, v);
+  }
+  cl.sync();
+  for (int ch = tid; ch < C; ch += blockDim.x) {
+    float ra[8], rx[8];   // remote loads first, adds after (one DSMEM round trip)
+#pragma unroll
+    for (int rk = 0; rk < 8; ++rk)
+      if (rk < CS) {
+        const float* rc = cl.map_shared_rank(chs, rk);
+        ra[rk] = rc[ch];
+        rx[rk] = rc[C + ch];
+      }
+    float sa = 0.f, sx = 0.f;
+#pragma unroll
+    for (int rk = 0; rk < 8; ++rk)
+      if (rk < CS) { sa += ra[rk]; sx += rx[rk]; }
+    // sum dz*xhat = rstd * (sum dz*x - mean * sum dz)
+    const int g = ch / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    const float sq = rstd * (sx - mean * sa);
+    tot[ch] = sa;
+    tot[C + ch] = sq;
+    if (rank == 0) {
+      atomicAdd(dbeta + ch, sa);
+      atomicAdd(dgamma + ch, sq);
+    }
+  }
+  cl.barrier_arrive();
+  __syncthreads();
+  for (int g = tid; g < G; g += blockDim.x) {
+    double ga = 0.0, gq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      ga += (double)gamma[c] * (double)tot[c];
+      gq += (double)gamma[c] * (double)tot[C + c];
+    }
+    const double n = (double)HW * cpg;
+    gab[2 * g] = (float)(ga / n);
+    gab[2 * g + 1] = (float)(gq / n);
+  }
+  __syncthreads();
+  float c1[8], c0[8], so[1][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k, g = ch / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    const float gA = gab[2 * g], gB = gab[2 * g + 1];
+    c1[k] = -rstd * rstd * gB;
+    c0[k] = rstd * (mean * rstd * gB - gA);
+    so[0][k] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < VMAX; ++i) {
+    const int p = p0 + r + i * rows;
+    if (p < p1) {
+      const int64_t row = rb + p;
+      float fx[8], fd[8], fa[8];
+      unpack8(hx[i], fx);
+      unpack8(hd[i], fd);
+      if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float dz = fd[k];
+        float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
+        if (add) o += fa[k];
+        fx[k] = o;
+        so[0][k] += o;
+      }
+      *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+    }
+  }
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
+    const int64_t row = rb + p;
+    float fx[8], fd[8], fa[8];
+    unpack8(*reinterpret_cast<const half8*>(x + row * ldx + v * 8), fx);
+    unpack8(*reinterpret_cast<const half8*>(dy + row * lddy + v * 8), fd);
+    if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      float dz = fd[k];
+      if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+      float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
+      if (add) o += fa[k];
+      fx[k] = o;
+      so[0][k] += o;
+    }
+    *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+  }
+  cl.barrier_wait();  // every CTA has finished reading chs[]
+  if (gsum) {         // uniform across the cluster
+    gn_block_channel_sums<1>(red, chs2, so, rows, C8, C, r, v);  // red[] was last read before the cluster barrier above
+    cl.sync();
+    for (int ch = rank * blockDim.x + tid; ch < C; ch += CS * blockDim.x) {
+      float ra[8];
+#pragma unroll
+      for (int rk = 0; rk < 8; ++rk)
+        if (rk < CS) ra[rk] = cl.map_shared_rank(chs2, rk)[ch];
+      float sa = 0.f;
+#pragma unroll
+      for (int rk = 0; rk < 8; ++rk)
+        if (rk < CS) sa += ra[rk];
+      gsum[(int64_t)b * ld_gsum + ch] = sa;
+    }
+    cl.sync();
+  }
+}
+
 }  // namespace bd
 
 using namespace bd;
+
+// Geometry of the cluster kernels: threads = C8 * rows (<= max_threads: 512 forward, 256 backward -- the backward kernel needs 128 registers), cluster size = the smallest of {1,2,4,8} that lets a
+// thread keep its share of the sample in GN_VMAX register vectors (grown while the grid would not fill the GPU).
+// Returns false when the sample is too large for one cluster to be a sensible unit (CelebA-HQ resolutions at small
+// batch): the three-kernel path, which splits a sample over many independent CTAs, serves those.
+static int gn_env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+static bool gn_fused_geometry(int B, int HW, int C, int max_threads, int vmax, int* threads, int* cs) {
+  if (getenv("BD_GN_V1")) return false;
+  const int C8 = C / 8;
+  if (C8 > max_threads || C8 < 1) return false;
+  int rows = max_threads / C8;
+  if (rows > HW) rows = HW;
+  if (rows < 1) rows = 1;
+  *threads = C8 * rows;
+  int c = 1;
+  while (c < 8 && ceil_div(ceil_div(HW, c), rows) > vmax) c *= 2;
+  while (c < 8 && (int64_t)B * c < num_sms() && HW / (2 * c) >= rows) c *= 2;
+  if (ceil_div(ceil_div(HW, c), rows) > 32) return false;
+  *cs = c;
+  return true;
+}
+
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int threads, size_t smem, int cs, cudaStream_t st,
+                                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 extern "C" {
 
@@ -312,6 +717,21 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && C <= 2048,
                "bd_groupnorm_fwd: need C %% 8 == 0, C %% G == 0, ld %% 8 == 0, C <= 2048 (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
+  {
+    int fthreads, cs;
+    const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;
+    if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_FT", 256), vmax, &fthreads, &cs) &&
+        (size_t)fthreads * 64 >= (size_t)cs * 2 * G * sizeof(double)) {   // red[] doubles as the peer-partials gather buffer
+      const size_t smem = (size_t)fthreads * 64 + (size_t)2 * C * 4 + (size_t)2 * G * 8 + (size_t)2 * G * 4;
+      cudaError_t e = launch_cluster(vmax == 4 ? gn_fwd_fused_kernel<4> : gn_fwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
+                                     cs, (cudaStream_t)stream, (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, stats,
+                                     HW, C, G, eps, apply_silu);
+      if (e != cudaSuccess) { set_error("bd_groupnorm_fwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+      count_launch(1);
+      BD_CHECK_LAUNCH();
+      return BD_OK;
+    }
+  }
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 4, &threads, &rows, &splits, &asplits);
   gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
@@ -328,12 +748,28 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
 
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
-                     float* dbeta, float* work, int B, int HW, int C, int G, int apply_silu, void* stream) {
+                     float* dbeta, float* work, float* gsum, int64_t ld_gsum, int B, int HW, int C, int G, int apply_silu,
+                     void* stream) {
   BD_CHECK_ARG(x && dy && dx && gamma && beta && stats && dgamma && dbeta && work, "bd_groupnorm_bwd: null pointer");
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && C <= 2048 &&
                    (!add_dx || ld_add % 8 == 0),
                "bd_groupnorm_bwd: bad shape (C=%d G=%d)", C, G);
   if (B == 0) return BD_OK;
+  {
+    int fthreads, cs;
+    const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;
+    if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs)) {
+      const size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
+      cudaError_t e = launch_cluster(vmax == 4 ? gn_bwd_fused_kernel<4> : gn_bwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
+                                     cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
+                                     (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
+                                     gsum, ld_gsum, HW, C, G, apply_silu);
+      if (e != cudaSuccess) { set_error("bd_groupnorm_bwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+      count_launch(1);
+      BD_CHECK_LAUNCH();
+      return BD_OK;
+    }
+  }
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 3, &threads, &rows, &splits, &asplits);
   gn_bwd_reduce_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
@@ -346,6 +782,10 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
       stats, gab, HW, C, G, asplits, apply_silu);
   count_launch(3);
   BD_CHECK_LAUNCH();
+  if (gsum) {
+    cudaMemset2DAsync(gsum, (size_t)ld_gsum * sizeof(float), 0, (size_t)C * sizeof(float), B, (cudaStream_t)stream);
+    return bd_colsum_f16(dx, ld_dx, gsum, ld_gsum, B, HW, C, 1, stream);
+  }
   return BD_OK;
 }
 

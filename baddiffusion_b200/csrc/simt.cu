@@ -217,6 +217,22 @@ __global__ void __launch_bounds__(256) simt_wgrad_kernel(ConvGeom g, const __hal
   }
 }
 
+// Batched bias gradients: job j = {gsum (B, ld) f32, ld, dst (C) f32, C}; dst[c] += sum_b gsum[b][c] in sample order.
+// gsum rows are what the GroupNorm backward leaves behind (norm.cu), so every conv/linear bias gradient of the UNet is
+// produced by ONE launch instead of one column-sum pass over its activation gradient each.
+__global__ void __launch_bounds__(256) bias_from_gsum_kernel(const long long* __restrict__ jobs, int B) {
+  const long long* j = jobs + 4 * (size_t)blockIdx.y;
+  const float* g = reinterpret_cast<const float*>(j[0]);
+  const int64_t ld = j[1];
+  float* dst = reinterpret_cast<float*>(j[2]);
+  const int C = (int)j[3];
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int b = 0; b < B; ++b) s += g[(int64_t)b * ld + c];
+  dst[c] += s;
+}
+
 // out[b][c] (+)= sum_{p in sample b} x[b,p,c]   (rows_per_b = HW; rows_per_b = all rows with B=1 for a bias grad)
 // grid (C8-blocks, B, splits) -> atomics over splits
 __global__ void __launch_bounds__(256) colsum_kernel(const __half* __restrict__ x, int64_t ldx, float* __restrict__ out,
@@ -718,6 +734,15 @@ int bd_colsum_f16(const void* x, int64_t ld_x, float* out, int64_t ld_out, int B
   if (cs > (int)((rows_per_b + 63) / 64)) cs = (int)((rows_per_b + 63) / 64);
   if (cs < 1) cs = 1;
   colsum_kernel<<<dim3(ceil_div(C, 256), B, cs), 256, 0, st>>>((const __half*)x, ld_x, out, ld_out, rows_per_b, C, cs);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_bias_from_gsum(const void* jobs, int njobs, int max_c, int B, void* stream) {
+  BD_CHECK_ARG(jobs && njobs >= 0 && max_c > 0 && B > 0, "bd_bias_from_gsum: bad argument");
+  if (njobs == 0) return BD_OK;
+  bias_from_gsum_kernel<<<dim3(ceil_div(max_c, 256), njobs), 256, 0, (cudaStream_t)stream>>>((const long long*)jobs, B);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -23,7 +23,16 @@ constexpr int C3_BSTAGES = 3;
 constexpr int C3_A_STAGE_BYTES = 82 * 1024;           // >= 18*18*2*128 = 82,944 and 18*34*128 = 78,336
 constexpr int C3_B_STAGE_BYTES = C3_BN * C3_BK * 2;   // 16 KB
 constexpr int C3_BAR_OFFSET = C3_ASTAGES * C3_A_STAGE_BYTES + C3_BSTAGES * C3_B_STAGE_BYTES;
-constexpr int C3_SMEM = C3_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3_BSTAGES + 1) * 8 + 16 + 1024;
+// persistent kernel (H % 32 == 0 only): tighter halo stages make room for the epilogue's transpose tiles
+constexpr int C3P_A_STAGE_BYTES = 77 * 1024;          // >= 18*34*128 = 78,336
+constexpr int C3P_EPI_PITCH = 80;                     // bytes per staged pixel row (32 channels = 64 B + 16 B: conflict-free stmatrix)
+constexpr int C3P_EPI_BYTES = 16 * 16 * C3P_EPI_PITCH;  // 16 warps x 16 pixels
+constexpr int C3P_B_OFFSET = C3_ASTAGES * C3P_A_STAGE_BYTES;
+constexpr int C3P_EPI_OFFSET = C3P_B_OFFSET + C3_BSTAGES * C3_B_STAGE_BYTES;
+constexpr int C3P_BAR_OFFSET = C3P_EPI_OFFSET + C3P_EPI_BYTES;
+constexpr int C3P_SMEM = C3P_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3_BSTAGES + 2) * 8 + 16 + 1024;
+static_assert(C3P_SMEM <= 232448, "conv3p shared memory");
+constexpr int C3_SMEM = C3_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3_BSTAGES + 2) * 8 + 16 + 1024;
 
 struct Conv3Params {
   int MB;                                   // MMA blocks in the region
@@ -254,7 +263,32 @@ int conv3_supported(const Conv3Call& c) {
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
                   Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st);
 
-int conv3_launch(const Conv3Call& c, cudaStream_t st) {
+// 512 x 512 fp16 identity: the weight of the "residual" K-segment of the persistent kernel.  y = conv(x) + r is run as
+// conv(x) + I * r on the tensor cores (exact: products by 1.0 accumulate in fp32), so the epilogue never has to gather
+// the residual in the accumulator's channel-per-lane layout (measured: 31 kcycles per tile as strided 2-byte loads).
+constexpr int C3_ID_N = 512;
+static __half* g_identity = nullptr;
+__global__ void fill_identity_kernel(__half* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n * n) p[i] = __float2half((i / n == i % n) ? 1.0f : 0.0f);
+}
+const __half* conv3_identity() {   // called from bd_init(): never inside a graph capture
+  if (!g_identity) {
+    if (cudaMalloc(&g_identity, (size_t)C3_ID_N * C3_ID_N * sizeof(__half)) != cudaSuccess) { g_identity = nullptr; return nullptr; }
+    fill_identity_kernel<<<ceil_div(C3_ID_N * C3_ID_N, 256), 256>>>(g_identity, C3_ID_N);
+    cudaDeviceSynchronize();
+  }
+  return g_identity;
+}
+
+int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
+  Conv3Call c = c_in;
+  if (c.residual && !c.a2 && !c.b_mn && !c.out_f32 && c.H % 32 == 0 && c.N <= C3_ID_N && c.N % 64 == 0 && g_identity &&
+      !getenv("BD_NO_CONV3P") && !getenv("BD_NO_CONV3T") && !getenv("BD_NO_RES_ID")) {
+    c.a2 = c.residual; c.ld_a2 = c.ld_res; c.Ca2 = c.N;
+    c.b2 = g_identity; c.ld_b2 = C3_ID_N;
+    c.residual = nullptr;
+  }
   Conv3Params p;
   memset(&p, 0, sizeof(p));
   if (!conv3_geometry(c.H, c.W, &p)) { set_error("conv3 halo kernel: unsupported geometry %dx%d", c.H, c.W); return BD_ERR_UNSUPPORTED; }
@@ -523,9 +557,303 @@ __global__ void __launch_bounds__(576, 1) umma_conv3t_kernel(const __grid_consta
   }
 }
 
+// =============================================================================================================
+// Persistent variant of the transposed kernel (the default for H % 32 == 0).  One CTA per SM walks a strided list of
+// 128-channel x 512-pixel tiles:
+//   * the producer warp runs ahead across tile boundaries (both halo stages and the weight ring are refilled while
+//     the previous tile is still in its epilogue), so the first MMA of a tile never waits for a cold pipeline, and
+//     the TMEM allocation / barrier set-up / tensor-map prefetch are paid once per SM instead of once per tile;
+//   * the epilogue goes straight from TMEM to global memory: a TMEM lane is an output CHANNEL, so the 32 lanes of a
+//     warp hold 32 consecutive channels of one pixel and every st.global.b16 of the warp is one full 64-byte run of
+//     a pixel row -- no shared-memory transpose, no named barriers (the staged epilogue of umma_conv3t_kernel cost
+//     ~14 kcycles per tile against 18.4 kcycles of MMA issue);
+//   * accumulators are handed back to the MMA warp through a tmem_empty barrier (16 epilogue warps arrive).
+// TMEM is full with one tile (2 x 256 fp32 columns), so epilogue and MMA of consecutive tiles do not overlap; a
+// 256-pixel tile would double-buffer but doubles the weight traffic per MAC to ~41 B/clk/SM, above what L2 sustains.
+// =============================================================================================================
+template <bool A_MN>
+__global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                             const __grid_constant__ CUtensorMap tmX1,
+                                                             const __grid_constant__ CUtensorMap tmW0,
+                                                             const __grid_constant__ CUtensorMap tmW1,
+                                                             const Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem + C3P_B_OFFSET;
+  uint8_t* smem_epi = smem + C3P_EPI_OFFSET;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C3P_BAR_OFFSET);
+  uint64_t* a_empty = a_full + C3_ASTAGES;
+  uint64_t* b_full = a_empty + C3_ASTAGES;
+  uint64_t* b_empty = b_full + C3_BSTAGES;
+  uint64_t* tmem_full = b_empty + C3_BSTAGES;
+  uint64_t* tmem_empty = tmem_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_n = p.tiles_w * p.tiles_h * p.NB;  // pixel tiles per 128-channel slab
+  const int total = per_n * (p.N / C3_BN);
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmX1);
+    prefetch_tmap(&tmW0);
+    prefetch_tmap(&tmW1);
+    for (int s = 0; s < C3_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C3_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 16);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer: free-running over all tiles of this CTA =====
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+        const int n_tile = tile / per_n, rem = tile - n_tile * per_n;
+        const int tw = rem % p.tiles_w, th = (rem / p.tiles_w) % p.tiles_h, n0 = rem / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.reg_w, h0 = th * p.reg_h;
+        for (int seg = 0; seg < 2 && ok; ++seg) {
+          const int nkb = seg ? p.nkb2 : p.nkb;
+          const int ntap = seg ? 1 : 9;
+          const CUtensorMap* mapX = seg ? &tmX1 : &tmX0;
+          const CUtensorMap* mapW = seg ? &tmW1 : &tmW0;
+          for (int kb = 0; kb < nkb && ok; ++kb) {
+            ok = mbar_wait(&a_empty[as], aph ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            mbar_expect_tx(&a_full[as], p.a_bytes);
+            tma_load_4d(mapX, &a_full[as], smem + as * C3P_A_STAGE_BYTES, kb * C3_BK, w0 - 1, h0 - 1, n0);
+            for (int t = 0; t < ntap; ++t) {
+              ok = mbar_wait(&b_empty[bs], bph ^ 1, p.error_flag, 1);
+              if (!ok) break;
+              uint8_t* sw = smem_w + bs * C3_B_STAGE_BYTES;
+              mbar_expect_tx(&b_full[bs], C3_B_STAGE_BYTES);
+              if (!A_MN) {
+                tma_load_3d(mapW, &b_full[bs], sw, kb * C3_BK, n_tile * C3_BN, t);
+              } else {
+                tma_load_3d(mapW, &b_full[bs], sw, n_tile * C3_BN, kb * C3_BK, t);
+                tma_load_3d(mapW, &b_full[bs], sw + 64 * C3_BK * 2, n_tile * C3_BN + 64, kb * C3_BK, t);
+              }
+              if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+            }
+            if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0, tph = 0;
+      bool ok = true;
+      int di = 0;
+      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+        ok = mbar_wait(tmem_empty, tph ^ 1, p.error_flag, 4);  // accumulators drained by the previous epilogue
+        if (!ok) break;
+        tc_fence_after();
+        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di] = clock64();   // [4i]: tile i may start
+        bool first = true;
+        for (int seg = 0; seg < 2 && ok; ++seg) {
+          const int nkb = seg ? p.nkb2 : p.nkb;
+          const int ntap = seg ? 1 : 9;
+          for (int kb = 0; kb < nkb && ok; ++kb) {
+            ok = mbar_wait(&a_full[as], aph, p.error_flag, 2);
+            if (!ok) break;
+            const uint32_t sx = smem_u32(smem + as * C3P_A_STAGE_BYTES);
+            for (int t = 0; t < ntap; ++t) {
+              ok = mbar_wait(&b_full[bs], bph, p.error_flag, 2);
+              if (!ok) break;
+              tc_fence_after();
+              int dy = seg ? 0 : t / 3 - 1, dx = seg ? 0 : t % 3 - 1;
+              if (p.flip) { dy = -dy; dx = -dx; }
+              const uint32_t sw = smem_u32(smem_w + bs * C3_B_STAGE_BYTES);
+              const int tap_row = (dy + 1) * p.pitch + (dx + 1);
+#pragma unroll
+              for (int blk = 0; blk < 2; ++blk) {
+                const uint32_t x0 = sx + (uint32_t)(blk * 8 + tap_row) * 128u;
+#pragma unroll
+                for (int k = 0; k < C3_BK / 16; ++k) {
+                  const uint64_t wd = A_MN ? make_desc(sw + k * 2048, 512, 64) : make_desc(sw + k * 32, 1, 64);
+                  const uint64_t xd = make_desc(x0 + k * 32, 1, p.a_sbo);
+                  umma_f16(tmem_base + blk * 256, wd, xd, p.idesc, (first && k == 0) ? 0u : 1u);
+                }
+              }
+              first = false;
+              umma_commit(&b_empty[bs]);
+              if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+            }
+            if (ok) umma_commit(&a_empty[as]);
+            if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+          }
+        }
+        if (ok) umma_commit(tmem_full);
+        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di + 1] = clock64();  // [4i+1]: last MMA of tile i issued
+        di += 4;
+        tph ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: 4 groups of 4 warps; group g4 drains pixel half (g4 & 1) of block (g4 >> 1); warp quadrant q owns
+    // channels 32q..32q+31 (TMEM lanes), one channel per thread =====
+    const int q = warp & 3, g4 = (warp - 2) >> 2, blk = g4 >> 1, phalf = g4 & 1;
+    const int ch = q * 32 + lane;
+    uint32_t tph = 0;
+    bool ok = true;
+    int di = 0;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+      const int n_tile = tile / per_n, rem = tile - n_tile * per_n;
+      const int tw = rem % p.tiles_w, th = (rem / p.tiles_w) % p.tiles_h, n0 = rem / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.reg_w + blk * 8, h0 = th * p.reg_h;
+      const int gcol = n_tile * C3_BN + ch;
+      float badd = 0.f;
+      if (p.bias) badd += p.bias[gcol];
+      if (p.bias2) badd += p.bias2[gcol];
+      if (p.rowbias) badd += p.rowbias[(int64_t)n0 * p.ld_rowbias + gcol];
+      ok = mbar_wait(tmem_full, tph, p.error_flag, 3);
+      tph ^= 1;
+      if (!ok) break;
+      tc_fence_after();
+      const bool stamp = p.dbg && warp == 2 && lane == 0 && di < 60;
+      if (stamp) p.dbg[(size_t)blockIdx.x * 64 + di + 2] = clock64();   // [4i+2]: accumulators of tile i complete
+      if (!p.out_f32 && !p.residual) {
+        // ---- fp16 output: TMEM fragments -> f16x2 -> stmatrix.trans into a warp-private [16 px][32 ch] tile -> 16-byte
+        // read-back -> st.global.v4 (every warp store = 8 pixels x 64 contiguous bytes)
+        const int fr = lane >> 2;                 // fragment row: channels fr, fr+8 (+16, +24 for the upper half-quadrant)
+        float bq[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = n_tile * C3_BN + q * 32 + fr + 8 * i;
+          float b = 0.f;
+          if (p.bias) b += p.bias[c];
+          if (p.bias2) b += p.bias2[c];
+          if (p.rowbias) b += p.rowbias[(int64_t)n0 * p.ld_rowbias + c];
+          bq[i] = b;
+        }
+        const uint32_t stage = smem_u32(smem_epi + (warp - 2) * 16 * C3P_EPI_PITCH);
+        // stmatrix row address of this thread: matrix lane>>3 = {ch 0-7 | ch 8-15} x {px 0-7 | px 8-15}, row lane&7 = pixel
+        const uint32_t st_addr = stage + (uint32_t)(((lane & 7) + ((lane >> 4) & 1) * 8) * C3P_EPI_PITCH + ((lane >> 3) & 1) * 16);
+        const uint32_t rd_addr = stage + (uint32_t)((lane >> 2) * C3P_EPI_PITCH + (lane & 3) * 16);
+        const float sc = p.scale;
+        __half* ybase = reinterpret_cast<__half*>(p.y) + n_tile * C3_BN + q * 32 + (lane & 3) * 8;
+#pragma unroll 1
+        for (int j0 = phalf * 128; j0 < phalf * 128 + 128; j0 += 16) {
+          uint32_t va[8], vb[8];
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + j0;
+          tmem_ld_16x256b_x2_nowait(ta, va);
+          tmem_ld_16x256b_x2_nowait(ta + (16u << 16), vb);
+          tmem_wait_ld();
+          __syncwarp();   // the previous chunk's read-back is complete
+          stmatrix_x4_trans(st_addr,
+                            pack_f16x2((__uint_as_float(va[0]) + bq[0]) * sc, (__uint_as_float(va[1]) + bq[0]) * sc),
+                            pack_f16x2((__uint_as_float(va[2]) + bq[1]) * sc, (__uint_as_float(va[3]) + bq[1]) * sc),
+                            pack_f16x2((__uint_as_float(va[4]) + bq[0]) * sc, (__uint_as_float(va[5]) + bq[0]) * sc),
+                            pack_f16x2((__uint_as_float(va[6]) + bq[1]) * sc, (__uint_as_float(va[7]) + bq[1]) * sc));
+          stmatrix_x4_trans(st_addr + 32,
+                            pack_f16x2((__uint_as_float(vb[0]) + bq[2]) * sc, (__uint_as_float(vb[1]) + bq[2]) * sc),
+                            pack_f16x2((__uint_as_float(vb[2]) + bq[3]) * sc, (__uint_as_float(vb[3]) + bq[3]) * sc),
+                            pack_f16x2((__uint_as_float(vb[4]) + bq[2]) * sc, (__uint_as_float(vb[5]) + bq[2]) * sc),
+                            pack_f16x2((__uint_as_float(vb[6]) + bq[3]) * sc, (__uint_as_float(vb[7]) + bq[3]) * sc));
+          __syncwarp();
+          // chunk = image rows (j0>>3), (j0>>3)+1 of the block, 8 pixels each; this lane: pixel (lane>>2) of each row
+          const int64_t m0 = ((int64_t)n0 * p.H + h0 + (j0 >> 3)) * p.W + w0 + (lane >> 2);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(rd_addr + it * 8 * C3P_EPI_PITCH));
+            *reinterpret_cast<uint4*>(ybase + (m0 + (int64_t)it * p.W) * p.ld_y) = val;
+          }
+        }
+      } else {
+      const int ldr = (int)p.ld_res, ldy = (int)p.ld_y;
+#pragma unroll 1
+      for (int j0 = phalf * 128; j0 < phalf * 128 + 128; j0 += 16) {
+        uint32_t v[16];
+        tmem_ld16_nowait(tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + j0, v);
+        // pixel j of the block = (row j >> 3, column j & 7): this chunk is 2 image rows of 8 pixels
+        const int64_t m0 = ((int64_t)n0 * p.H + h0 + (j0 >> 3)) * p.W + w0;
+        unsigned short res[16];
+        if (p.residual) {
+          const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.residual) + m0 * p.ld_res + gcol;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            const unsigned short* rr = rp + (int64_t)r * p.W * p.ld_res;
+#pragma unroll
+            for (int px = 0; px < 8; ++px) res[r * 8 + px] = rr[px * ldr];
+          }
+        }
+        tmem_wait_ld();
+        if (p.out_f32) {
+          float* yp = reinterpret_cast<float*>(p.y) + m0 * p.ld_y + gcol;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            float* yr = yp + (int64_t)r * p.W * p.ld_y;
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+              float f = __uint_as_float(v[r * 8 + px]) + badd;
+              if (p.residual) f += __half2float(__ushort_as_half(res[r * 8 + px]));
+              yr[px * ldy] = f * p.scale;
+            }
+          }
+        } else {
+          __half* yp = reinterpret_cast<__half*>(p.y) + m0 * p.ld_y + gcol;
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+            __half* yr = yp + (int64_t)r * p.W * p.ld_y;
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+              float f = __uint_as_float(v[r * 8 + px]) + badd;
+              if (p.residual) f += __half2float(__ushort_as_half(res[r * 8 + px]));
+              yr[px * ldy] = __float2half_rn(f * p.scale);
+            }
+          }
+        }
+      }
+      }  // direct-store path (fp32 output / explicit residual)
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+      if (stamp) p.dbg[(size_t)blockIdx.x * 64 + di + 3] = clock64();   // [4i+3]: this warp's share of tile i stored
+      di += 4;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
                   Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st) {
   p.idesc = (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  if (!getenv("BD_NO_CONV3P")) {
+    // persistent kernel: one CTA per SM over all (channel slab, pixel tile) pairs, channel slab slowest so the CTAs
+    // that run together share their weight tiles in L2
+    const int total = (int)(grid.x * grid.y);
+    const int ctas = total < num_sms() ? total : num_sms();
+    static bool pattr[2] = {false, false};
+    if (a_mn) {
+      if (!pattr[1]) { cudaFuncSetAttribute(umma_conv3p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[1] = true; }
+      umma_conv3p_kernel<true><<<ctas, 576, C3P_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+    } else {
+      if (!pattr[0]) { cudaFuncSetAttribute(umma_conv3p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[0] = true; }
+      umma_conv3p_kernel<false><<<ctas, 576, C3P_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+    }
+    count_launch(1);
+    return BD_OK;
+  }
   static bool attr_set[2] = {false, false};
   if (a_mn) {
     if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }

@@ -24,12 +24,15 @@ from .unet import resnet_prefixes, topology
 
 class Act:
     """An activation view and (training) the matching gradient view; g_filled is build-time bookkeeping: whether
-    some consumer's backward has already written the gradient (later contributions must add)."""
+    some consumer's backward has already written the gradient (later contributions must add).  gs is a (B, C) fp32
+    view that the GroupNorm backward fills with the per-sample channel sums of the FINAL gradient (gs_valid tracks, in
+    backward order, whether the last writer of g was such a GroupNorm): the producer's bias gradient without a pass
+    over g."""
 
-    __slots__ = ("t", "g", "g_filled")
+    __slots__ = ("t", "g", "g_filled", "gs", "gs_valid")
 
-    def __init__(self, t, g=None):
-        self.t, self.g, self.g_filled = t, g, False
+    def __init__(self, t, g=None, gs=None):
+        self.t, self.g, self.g_filled, self.gs, self.gs_valid = t, g, False, gs, False
 
     @property
     def C(self):
@@ -56,6 +59,7 @@ class UNetEngine:
         self._bwd_emitters: List[Callable[[], None]] = []
         self._pool: Dict[tuple, torch.Tensor] = {}
         self.io: Dict[str, torch.Tensor] = {}
+        self._bias_jobs: List[tuple] = []   # (gs view, bias-gradient view): one batched launch at the end of backward
         self.named: Dict[str, Act] = {}  # layer prefix -> output (introspection / parity debugging)
         self.flat16 = model.flat_half()
         self.flat32 = model.flat_params
@@ -105,7 +109,18 @@ class UNetEngine:
         a = Act(self.tmp(H, C, tag))
         if self.train:
             a.g = self.new(H, C)
+            a.gs = torch.empty(self.B, C, device=self.dev)
         return a
+
+    def _bias_from(self, out: Act, *grads):
+        """Bias gradients of the layer that produced `out`: from out.gs when the last writer of out.g left the channel
+        sums there (returns True: the caller skips its own column-sum pass), else False."""
+        if out.gs is None or not out.gs_valid or os.environ.get("BD_NO_GSUM"):
+            return False
+        for g in grads:
+            if g is not None:
+                self._bias_jobs.append((out.gs, g))
+        return True
 
     # ------------------------------------------------------------------ side stream (parameter gradients)
     def _fork(self, fn: Callable[[], None]):
@@ -181,10 +196,13 @@ class UNetEngine:
             for (ri, sk, co) in b["resnets"]:
                 k = len(skip_specs) - 1 - n
                 assert skip_specs[k] == (sk, Hu), (skip_specs[k], sk, Hu)
-                cat = Act(self.new(Hu, ri + sk), self.new(Hu, ri + sk) if self.train else None)
+                cat = Act(self.new(Hu, ri + sk), self.new(Hu, ri + sk) if self.train else None,
+                          torch.empty(B, ri + sk, device=dev) if self.train else None)
                 cats.append(cat)
-                x_slots.append(Act(cat.t[..., :ri], cat.g[..., :ri] if self.train else None))
-                skip_acts[k] = Act(cat.t[..., ri:], cat.g[..., ri:] if self.train else None)
+                x_slots.append(Act(cat.t[..., :ri], cat.g[..., :ri] if self.train else None,
+                                   cat.gs[:, :ri] if self.train else None))
+                skip_acts[k] = Act(cat.t[..., ri:], cat.g[..., ri:] if self.train else None,
+                                   cat.gs[:, ri:] if self.train else None)
                 n += 1
             if b["up"]:
                 Hu *= 2
@@ -260,6 +278,12 @@ class UNetEngine:
         if self.train:
             for emit in reversed(self._bwd_emitters):
                 emit()
+            if self._bias_jobs:
+                rows = [[gs.data_ptr(), gs.stride(0), g.data_ptr(), g.numel()] for gs, g in self._bias_jobs]
+                self._bias_table = torch.tensor(rows, dtype=torch.int64, device=dev)
+                nj, maxc = len(rows), max(r[3] for r in rows)
+                # parameter gradients: with the other parameter-gradient kernels, before the final join
+                self.bwd.append(lambda: self._fork(lambda: ops.bias_from_gsum(self._bias_table, nj, maxc, B)))
 
     def _skip_of(self, n):
         return self._skips[len(self._skips) - 1 - n]
@@ -308,41 +332,46 @@ class UNetEngine:
             dcol = self.d_tproj[:, col: col + Cout]
             x_filled = x.g_filled
             dout = out.g
-            B = self.B
+            # conv2.bias / conv_shortcut.bias: channel sums of dout, already left in out.gs by dout's last writer
+            bias_done = self._bias_from(out, g["conv2.bias"], gbs)
+            gb2 = None if bias_done else g["conv2.bias"]
+            gbs_ = None if bias_done else gbs
+            xgs = x.gs
 
             def wg2():
                 # conv2 (+ shortcut) parameter gradients
-                ops.conv_wgrad(a2, dout, g["conv2.weight"], g["conv2.bias"], ksize=3, accumulate=True, impl=impl)
+                ops.conv_wgrad(a2, dout, g["conv2.weight"], gb2, ksize=3, accumulate=True, impl=impl)
                 if has_sc:
-                    ops.conv_wgrad(x.t, dout, gws, gbs, ksize=1, accumulate=True, impl=impl)
+                    ops.conv_wgrad(x.t, dout, gws, gbs_, ksize=1, accumulate=True, impl=impl)
 
             def wg1():
-                # temb projection: per-sample column sums (resnet.py:577-580 broadcast add)
-                ops.colsum_f16(d_h1.view(B, H * H, Cout), dcol, H * H, B, accumulate=True)
-                # d(conv1.bias) == d(time_emb_proj.bias): both are the column sums above, added once in _emit_temb_bwd
+                # d(conv1.bias) == d(time_emb_proj.bias) == column sums of d_tproj, added once in _emit_temb_bwd
                 ops.conv_wgrad(a1, d_h1, g["conv1.weight"], None, ksize=3, accumulate=True, impl=impl)
 
             def bw():
                 self._fork(wg2)
                 ops.conv_dgrad(dout, w2, d_a2, ksize=3, impl=impl)
-                ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True)
+                # gsum = per-sample channel sums of d_h1 = gradient of the temb projection (resnet.py:577-580 broadcast add)
+                ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True, gsum=dcol)
                 self._fork(wg1)
                 ops.conv_dgrad(d_h1, w1, d_a1, ksize=3, impl=impl)
                 # input gradient: residual / shortcut branch + norm1 branch (+ whatever is already there)
                 if has_sc:
                     ops.conv_dgrad(dout, ws, x.g, ksize=1, residual=x.g if x_filled else None, impl=impl)
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g)
+                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g, gsum=xgs)
                 elif x_filled:
                     ops.add_f16(x.g, dout, x.g)
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g)
+                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g, gsum=xgs)
                 else:
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=dout)
+                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=dout, gsum=xgs)
 
             self.bwd.append(bw)
             x.g_filled = True
+            x.gs_valid = xgs is not None
             if cat_children:
                 for c in cat_children:
                     c.g_filled = True
+                    c.gs_valid = xgs is not None
 
         self._bwd_emitters.append(emit)
 
@@ -393,9 +422,11 @@ class UNetEngine:
             d_a = self.scratch(H, C, "daa")
             x_filled = x.g_filled
             dout = out.g
+            g_bp_ = None if self._bias_from(out, g_bp) else g_bp
+            xgs = x.gs
 
             def bw():
-                self._fork(lambda: ops.conv_wgrad(ao, dout, g_wp, g_bp, ksize=1, accumulate=True, impl=impl))
+                self._fork(lambda: ops.conv_wgrad(ao, dout, g_wp, g_bp_, ksize=1, accumulate=True, impl=impl))
                 ops.conv_dgrad(dout, wp, d_ao, ksize=1, impl=impl)
                 ops.attention_bwd(qkv.view(B, S, 3 * C), probs, d_ao.view(B, S, C), d_qkv.view(B, S, 3 * C), work, B, S, C,
                                   heads, sm_scale, impl=impl)
@@ -403,12 +434,13 @@ class UNetEngine:
                 ops.conv_dgrad(d_qkv, wqkv, d_a, ksize=1, impl=impl)
                 if x_filled:
                     ops.add_f16(x.g, dout, x.g)
-                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=x.g)
+                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=x.g, gsum=xgs)
                 else:
-                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=dout)
+                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=dout, gsum=xgs)
 
             self.bwd.append(bw)
             x.g_filled = True
+            x.gs_valid = xgs is not None
 
         self._bwd_emitters.append(emit)
 
@@ -427,14 +459,16 @@ class UNetEngine:
             gw_, gb_ = self.G32(p + "weight"), self.G32(p + "bias")
             x_filled = x.g_filled
             dout = out.g
+            gb__ = None if self._bias_from(out, gb_) else gb_
 
             def bw():
-                self._fork(lambda: ops.conv_wgrad(x.t, dout, gw_, gb_, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad,
+                self._fork(lambda: ops.conv_wgrad(x.t, dout, gw_, gb__, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad,
                                                   accumulate=True))
                 ops.conv_dgrad(dout, w, x.g, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad, residual=x.g if x_filled else None)
 
             self.bwd.append(bw)
             x.g_filled = True
+            x.gs_valid = False  # last writer is the strided dgrad
 
         self._bwd_emitters.append(emit)
 
@@ -458,14 +492,16 @@ class UNetEngine:
             d_u = self.scratch(2 * H, C, "dup")
             dout = out.g
             assert not x.g_filled
+            gb__ = None if self._bias_from(out, gb_) else gb_
 
             def bw():
-                self._fork(lambda: ops.conv_wgrad(u, dout, gw_, gb_, ksize=3, accumulate=True, impl=impl))
+                self._fork(lambda: ops.conv_wgrad(u, dout, gw_, gb__, ksize=3, accumulate=True, impl=impl))
                 ops.conv_dgrad(dout, w, d_u, ksize=3, impl=impl)
                 ops.upsample2x_bwd(d_u, x.g)
 
             self.bwd.append(bw)
             x.g_filled = True
+            x.gs_valid = False
 
         self._bwd_emitters.append(emit)
 
@@ -496,10 +532,11 @@ class UNetEngine:
 
             def bw():
                 ops.conv_out_bwd(a, w, self.io["d_eps"], d_a, g_w, g_b, accumulate=True)
-                ops.groupnorm_bwd(x.t, d_a, x.g, nw, nb, st, g_nw, g_nb, gw, G, True)
+                ops.groupnorm_bwd(x.t, d_a, x.g, nw, nb, st, g_nw, g_nb, gw, G, True, gsum=x.gs)
 
             self.bwd.append(bw)
             x.g_filled = True
+            x.gs_valid = x.gs is not None
 
         self._bwd_emitters.append(emit)
 
@@ -525,7 +562,7 @@ class UNetEngine:
         dt = self.d_tproj
 
         def bw():
-            self._join()  # the column sums in d_tproj (and every parameter gradient) come from the side stream
+            # d_tproj was filled (overwritten, column block by column block) by the norm2 GroupNorm backwards
             # time_emb_proj: y = silu(emb) @ Wtp^T + b
             ops.sgemm(dt, 1, ncol, self.emb, temb_dim, 1, g_wtp, temb_dim, 1, ncol, temb_dim, B, accumulate=True, act=2)
             ops.sgemm(ones, 0, 1, dt, ncol, 1, g_btp, 0, 1, 1, ncol, B, accumulate=True)
@@ -540,7 +577,6 @@ class UNetEngine:
             # linear_1: h1 = sin @ W1^T + b1
             ops.sgemm(d_h1, 1, temb_dim, self.sin, dim0, 1, g_w1, dim0, 1, temb_dim, dim0, B, accumulate=True)
             ops.sgemm(ones, 0, 1, d_h1, temb_dim, 1, g_b1, 0, 1, 1, temb_dim, B, accumulate=True)
-            dt.zero_()  # ready for the next step's column sums (memset node; graph-capturable)
 
         self.bwd.append(bw)
 

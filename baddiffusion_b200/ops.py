@@ -102,15 +102,20 @@ def groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, silu):
                                    float(eps), int(silu), _s()))
 
 
-def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None):
+def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None):
+    """gsum: optional (B, C) f32 view (row stride free) that receives the per-sample channel sums of dx."""
     px, ldx, B, H, W, Cc = _view(x)
     pdy, lddy, *_ = _view(dy)
     pdx, lddx, *_ = _view(dx)
     pa, lda = (None, 0)
     if add_dx is not None:
         pa, lda, *_ = _view(add_dx)
+    pg, ldg = (None, 0)
+    if gsum is not None:
+        assert gsum.dtype == torch.float32 and gsum.shape == (B, Cc) and gsum.stride(1) == 1
+        pg, ldg = gsum.data_ptr(), gsum.stride(0)
     check(L.lib().bd_groupnorm_bwd(px, ldx, pdy, lddy, pa, lda, pdx, lddx, _p(gamma), _p(beta), _p(stats), _p(dgamma),
-                                   _p(dbeta), _p(work), B, H * W, Cc, G, int(silu), _s()))
+                                   _p(dbeta), _p(work), pg, ldg, B, H * W, Cc, G, int(silu), _s()))
 
 
 def _conv_args(x, w, y, Cin, Cout, ksize, mode, pad, bias, bias2, rowbias, residual, x2, w2, scale, impl, geom=None):
@@ -165,6 +170,11 @@ def pack_conv_weight(w_oihw, out_f32=None, out_f16=None):
 
 def cast_f32_to_f16(src, dst):
     check(L.lib().bd_cast_f32_to_f16(_p(src), _p(dst), src.numel(), _s()))
+
+
+def bias_from_gsum(jobs, njobs, max_c, B):
+    """jobs: int64 (njobs, 4) device tensor of {gsum ptr, ld, dst ptr, C}; dst[c] += sum_b gsum[b, c]."""
+    check(L.lib().bd_bias_from_gsum(_p(jobs), njobs, max_c, B, _s()))
 
 
 def colsum_f16(x, out, rows_per_b, B, accumulate=False):

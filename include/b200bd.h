@@ -113,7 +113,10 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
  * work: bd_gn_workspace_floats(B, C) floats.                                                          */
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
-                     float* dbeta, float* dgb_work, int B, int HW, int C, int G, int apply_silu, void* stream);
+                     float* dbeta, float* dgb_work,
+                     float* gsum /* nullable: (B, C) f32 with row stride ld_gsum, OVERWRITTEN with the per-sample
+                                    channel sums of dx = the bias / time_emb_proj gradient of x's producer */,
+                     int64_t ld_gsum, int B, int HW, int C, int G, int apply_silu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1/K2/K3/K6/K9/K10  convolution / linear as (implicit) GEMM on fp16 NHWC views, fp32 accumulate.
@@ -167,6 +170,9 @@ int bd_cast_f32_to_f16(const float* src, void* dst, size_t n, void* stream);
 /* out[b][c] (+)= sum over the rows of sample b of x (f16 view): per-sample temb gradients and bias gradients */
 int bd_colsum_f16(const void* x, int64_t ld_x, float* out, int64_t ld_out, int B, int64_t rows_per_b, int C,
                   int accumulate, void* stream);
+/* every bias gradient of the plan in one launch: jobs = DEVICE array of njobs x 4 int64 {gsum pointer (B rows of f32,
+ * row stride ld), ld, dst pointer (C f32), C}; dst[c] += sum_b gsum[b][c].  gsum rows come from bd_groupnorm_bwd.   */
+int bd_bias_from_gsum(const void* jobs, int njobs, int max_c, int B, void* stream);
 /* dx = dy * silu'(x) (f32), n elements: backward of the SiLUs in the timestep MLP */
 int bd_silu_bwd_f32(const float* dy, const float* x, float* dx, size_t n, void* stream);
 /* y_f16 = silu(x_f32) */

@@ -175,9 +175,44 @@ def test_groupnorm_fwd_bwd(ops, B, C, H, silu):
     ref.backward(dyr)
     dx = torch.empty_like(x)
     dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
-    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dg, db, work, G, silu, add_dx=add)
+    gsum_wide = torch.full((B, C + 8), 7.0, device="cuda")
+    gsum = gsum_wide[:, :C]  # strided rows: the engine points this at column slices of wider buffers
+    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dg, db, work, G, silu, add_dx=add, gsum=gsum)
     assert (to_nchw(dx) - (xr.grad + addr)).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
     assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+    # per-sample channel sums of dx (bias / time_emb_proj gradients of the producer of x)
+    ref_sum = (xr.grad + addr).sum(dim=(2, 3))
+    assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05
+    assert bool((gsum_wide[:, C:] == 7.0).all())
+
+
+@pytest.mark.parametrize("B,C,H", [(128, 128, 32), (128, 256, 16), (128, 384, 32), (130, 512, 8), (4, 128, 64), (2, 128, 256)])
+def test_groupnorm_cluster_geometries(ops, B, C, H):
+    """Every cluster size / register-cache regime of the single-launch kernels (and the three-kernel path that serves
+    CelebA-HQ-sized samples) against torch, plus run-to-run bitwise reproducibility of the forward."""
+    torch.manual_seed(1)
+    G, eps = 32, 1e-6
+    x = (torch.randn(B, H, H, C, device="cuda") * 1.5 + 0.3).half()
+    gamma = torch.randn(C, device="cuda") * 0.2 + 1
+    beta = torch.randn(C, device="cuda") * 0.2
+    y, y2 = torch.empty_like(x), torch.empty_like(x)
+    stats = torch.empty(B, G, 2, device="cuda")
+    work = torch.empty(ops.gn_workspace_floats(B, C), device="cuda")
+    ops.groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, True)
+    ops.groupnorm_fwd(x, y2, gamma, beta, stats, work, G, eps, True)
+    assert torch.equal(y, y2)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    ref = F.silu(F.group_norm(xr, G, gamma, beta, eps))
+    assert (y.float().permute(0, 3, 1, 2) - ref).abs().max() < 2e-3 * max(1.0, float(ref.abs().max()))
+    dy = torch.randn(B, H, H, C, device="cuda").half()
+    ref.backward(dy.float().permute(0, 3, 1, 2))
+    dx = torch.empty_like(x)
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    gsum = torch.empty(B, C, device="cuda")
+    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dg, db, work, G, True, gsum=gsum)
+    assert (dx.float().permute(0, 3, 1, 2) - xr.grad).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
+    ref_sum = xr.grad.sum(dim=(2, 3))
+    assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05 * H / 32
 
 
 # ------------------------------------------------------------------------------------------------
