@@ -262,6 +262,7 @@ int conv3_supported(const Conv3Call& c) {
 
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
                   Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st);
+int conv3w_launch_fwd(const Conv3Call& c, Conv3Params p, cudaStream_t st);
 
 // 512 x 512 fp16 identity: the weight of the "residual" K-segment of the persistent kernel.  y = conv(x) + r is run as
 // conv(x) + I * r on the tensor cores (exact: products by 1.0 accumulate in fp32), so the epilogue never has to gather
@@ -283,8 +284,9 @@ const __half* conv3_identity() {   // called from bd_init(): never inside a grap
 
 int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
   Conv3Call c = c_in;
-  if (c.residual && !c.a2 && !c.b_mn && !c.out_f32 && c.H % 32 == 0 && c.N <= C3_ID_N && c.N % 64 == 0 && g_identity &&
-      !getenv("BD_NO_CONV3P") && !getenv("BD_NO_CONV3T") && !getenv("BD_NO_RES_ID")) {
+  const bool wide16 = c.H == 16 && c.W == 16 && c.N % 256 == 0 && !getenv("BD_NO_CONV3W");
+  if (c.residual && !c.a2 && !c.b_mn && !c.out_f32 && c.N <= C3_ID_N && c.N % 64 == 0 && g_identity && !getenv("BD_NO_RES_ID") &&
+      (wide16 || (c.H % 32 == 0 && !getenv("BD_NO_CONV3P") && !getenv("BD_NO_CONV3T")))) {
     c.a2 = c.residual; c.ld_a2 = c.ld_res; c.Ca2 = c.N;
     c.b2 = g_identity; c.ld_b2 = C3_ID_N;
     c.residual = nullptr;
@@ -303,6 +305,7 @@ int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
   p.residual = (const __half*)c.residual; p.ld_res = c.ld_res; p.scale = c.scale;
   p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
   p.error_flag = error_flag();
+  if (wide16 && !c.residual) return conv3w_launch_fwd(c, p, st);
   {
     const char* e = getenv("BD_CONV3_DBG_PTR");  // device pointer of a (ctas x 64) int64 buffer, bring-up only
     p.dbg = e ? (long long*)strtoull(e, nullptr, 0) : nullptr;
@@ -861,6 +864,277 @@ int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensor
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
     umma_conv3t_kernel<false><<<grid, 576, C3_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+  }
+  count_launch(1);
+  return BD_OK;
+}
+
+// =============================================================================================================
+// 16 x 16 images (the UNet's second resolution, 37 % of its FLOPs): one CTA = ONE image x 256 output channels.
+//   D[pixel, cout]: A = 128 pixels (8 px x 16 rows, a shifted view of the image's halo tile), B = a 256 x 64 weight
+//   tile, so the MMAs are 128 x 256 x 16 -- 96 B/clk of shared-memory operand reads, which sustains the full issue
+//   rate; the 128 x 128 MMAs of umma_conv3_kernel need 128 B/clk and measured 77-110 cycles instead of 64.
+//   Two blocks (left / right half of the image) x 256 fp32 columns = all 512 TMEM columns.  The input image is
+//   fetched once for all 256 channels (the 128-channel kernel fetched it once per channel slab).
+//   Epilogue: TMEM fragments (tcgen05.ld 16x256b) -> +bias -> f16x2 -> stmatrix into a warp-private [32 px][32 ch]
+//   tile -> 16-byte read-back -> st.global.v4 (8 pixels x 64 contiguous bytes per warp store).
+// Used for forward (K-major weights) and dgrad (MN-major view of the same weights, taps flipped); the 1x1 shortcut /
+// identity-residual K segment works as in the other kernels.
+// =============================================================================================================
+constexpr int C3W_BN = 256;
+constexpr int C3W_A_STAGE_BYTES = 41 * 1024;            // >= 18*18*128 = 41,472
+constexpr int C3W_B_STAGE_BYTES = C3W_BN * C3_BK * 2;   // 32 KB
+constexpr int C3W_EPI_PITCH = 80;
+constexpr int C3W_EPI_WARP_BYTES = 32 * C3W_EPI_PITCH;  // [32 px][32 ch] f16, padded rows
+constexpr int C3W_B_OFFSET = C3_ASTAGES * C3W_A_STAGE_BYTES;
+constexpr int C3W_EPI_OFFSET = C3W_B_OFFSET + C3_BSTAGES * C3W_B_STAGE_BYTES;
+constexpr int C3W_BIAS_OFFSET = C3W_EPI_OFFSET + 16 * C3W_EPI_WARP_BYTES;
+constexpr int C3W_BAR_OFFSET = C3W_BIAS_OFFSET + C3W_BN * 4;
+constexpr int C3W_SMEM = C3W_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3_BSTAGES + 1) * 8 + 16 + 1024;
+static_assert(C3W_SMEM <= 232448, "conv3w shared memory");
+
+__device__ __forceinline__ void tmem_ld_16x256b_x4_nowait(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ void stmatrix_x4(uint32_t smem_row_addr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+  asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+               ::"r"(smem_row_addr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(576, 1) umma_conv3w_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                             const __grid_constant__ CUtensorMap tmA1,
+                                                             const __grid_constant__ CUtensorMap tmB0,
+                                                             const __grid_constant__ CUtensorMap tmB1,
+                                                             const Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_b = smem + C3W_B_OFFSET;
+  uint8_t* smem_epi = smem + C3W_EPI_OFFSET;
+  float* sbias = reinterpret_cast<float*>(smem + C3W_BIAS_OFFSET);
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C3W_BAR_OFFSET);
+  uint64_t* a_empty = a_full + C3_ASTAGES;
+  uint64_t* b_full = a_empty + C3_ASTAGES;
+  uint64_t* b_empty = b_full + C3_BSTAGES;
+  uint64_t* tmem_full = b_empty + C3_BSTAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.x, n_tile = blockIdx.y;   // image, 256-channel slab
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmB1);
+    for (int s = 0; s < C3_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C3_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + C3W_BN) {   // bias + bias2 + per-image row bias of this slab, once
+    const int c = n_tile * C3W_BN + (threadIdx.x - 64);
+    float b = 0.f;
+    if (p.bias) b += p.bias[c];
+    if (p.bias2) b += p.bias2[c];
+    if (p.rowbias) b += p.rowbias[(int64_t)n0 * p.ld_rowbias + c];
+    sbias[threadIdx.x - 64] = b;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        const CUtensorMap* mapA = seg ? &tmA1 : &tmA0;
+        const CUtensorMap* mapB = seg ? &tmB1 : &tmB0;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_empty[as], aph ^ 1, p.error_flag, 1);
+          if (!ok) break;
+          mbar_expect_tx(&a_full[as], p.a_bytes);
+          tma_load_4d(mapA, &a_full[as], smem + as * C3W_A_STAGE_BYTES, kb * C3_BK, -1, -1, n0);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_empty[bs], bph ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            uint8_t* sb = smem_b + bs * C3W_B_STAGE_BYTES;
+            mbar_expect_tx(&b_full[bs], C3W_B_STAGE_BYTES);
+            if (!B_MN) {
+              tma_load_3d(mapB, &b_full[bs], sb, kb * C3_BK, n_tile * C3W_BN, t);                    // box {64 k, 256 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)                                                            // 4 boxes {64 n, 64 k}
+                tma_load_3d(mapB, &b_full[bs], sb + j * 64 * C3_BK * 2, n_tile * C3W_BN + j * 64, kb * C3_BK, t);
+            }
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true, first = true;
+      for (int seg = 0; seg < 2 && ok; ++seg) {
+        const int nkb = seg ? p.nkb2 : p.nkb;
+        const int ntap = seg ? 1 : 9;
+        for (int kb = 0; kb < nkb && ok; ++kb) {
+          ok = mbar_wait(&a_full[as], aph, p.error_flag, 2);
+          if (!ok) break;
+          const uint32_t sa = smem_u32(smem + as * C3W_A_STAGE_BYTES);
+          for (int t = 0; t < ntap; ++t) {
+            ok = mbar_wait(&b_full[bs], bph, p.error_flag, 2);
+            if (!ok) break;
+            tc_fence_after();
+            int dy = seg ? 0 : t / 3 - 1, dx = seg ? 0 : t % 3 - 1;
+            if (p.flip) { dy = -dy; dx = -dx; }
+            const uint32_t sb = smem_u32(smem_b + bs * C3W_B_STAGE_BYTES);
+            const int tap_row = (dy + 1) * p.pitch + (dx + 1);
+#pragma unroll
+            for (int mb = 0; mb < 2; ++mb) {
+              const uint32_t a0 = sa + (uint32_t)(mb * 8 + tap_row) * 128u;   // block mb = image columns 8mb .. 8mb+7
+#pragma unroll
+              for (int k = 0; k < C3_BK / 16; ++k) {
+                const uint64_t ad = make_desc(a0 + k * 32, 1, p.a_sbo);
+                const uint64_t bd = B_MN ? make_desc(sb + k * 2048, 512, 64) : make_desc(sb + k * 32, 1, 64);
+                umma_f16(tmem_base + mb * C3W_BN, ad, bd, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+            }
+            first = false;
+            umma_commit(&b_empty[bs]);
+            if (++bs == C3_BSTAGES) { bs = 0; bph ^= 1; }
+          }
+          if (ok) umma_commit(&a_empty[as]);
+          if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+        }
+      }
+      if (ok) umma_commit(tmem_full);
+    }
+  } else {
+    // ===== epilogue: warp quadrant q = TMEM lanes (pixels) 32q.., column group cg = (warp-2)>>2: block cg>>1, channel
+    // half cg&1 (128 channels = 4 chunks of 32) =====
+    const int q = warp & 3, cg = (warp - 2) >> 2, blk = cg >> 1, chalf = cg & 1;
+    const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
+    tc_fence_after();
+    if (ok) {
+      const uint32_t stage = smem_u32(smem_epi + (warp - 2) * C3W_EPI_WARP_BYTES);
+      // stmatrix (non-transposed): matrix i = lane>>3 holds pixels (i&1)*8.. of the 16-lane half, channels (i>>1)*8..
+      const uint32_t st_row = (uint32_t)(((lane & 7) + ((lane >> 3) & 1) * 8) * C3W_EPI_PITCH + ((lane >> 4) & 1) * 16);
+      const uint32_t rd_addr = stage + (uint32_t)((lane >> 2) * C3W_EPI_PITCH + (lane & 3) * 16);
+      const float sc = p.scale;
+      const int fc = 2 * (lane & 3);   // fragment columns fc, fc+1 (+8j)
+      // pixel of TMEM lane r of block blk: row r>>3, column blk*8 + (r&7); read-back step `it` of this warp = image row 4q+it
+      __half* ybase = reinterpret_cast<__half*>(p.y) +
+                      (((int64_t)n0 * p.H + 4 * q) * p.W + blk * 8 + (lane >> 2)) * p.ld_y + n_tile * C3W_BN + chalf * 128 +
+                      (lane & 3) * 8;
+      float* ybase32 = reinterpret_cast<float*>(p.y) +
+                       (((int64_t)n0 * p.H + 4 * q) * p.W + blk * 8 + (lane >> 2)) * p.ld_y + n_tile * C3W_BN + chalf * 128 +
+                       (lane & 3) * 8;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        const int col = chalf * 128 + c0;                 // first channel of this chunk inside the 256-slab
+        __syncwarp();                                     // previous chunk's read-back is complete
+#pragma unroll
+        for (int lh = 0; lh < 2; ++lh) {                  // lanes (pixels) 0-15, 16-31 of the quadrant
+          uint32_t v[16];
+          tmem_ld_16x256b_x4_nowait(tmem_base + ((uint32_t)(q * 32 + lh * 16) << 16) + blk * C3W_BN + col, v);
+          tmem_wait_ld();
+          uint32_t m[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                   // channels col + 8j + fc, +1
+            const float2 b = *reinterpret_cast<const float2*>(sbias + col + 8 * j + fc);
+            m[2 * j] = pack_f16x2((__uint_as_float(v[4 * j]) + b.x) * sc, (__uint_as_float(v[4 * j + 1]) + b.y) * sc);
+            m[2 * j + 1] = pack_f16x2((__uint_as_float(v[4 * j + 2]) + b.x) * sc, (__uint_as_float(v[4 * j + 3]) + b.y) * sc);
+          }
+          const uint32_t base = stage + lh * 16 * C3W_EPI_PITCH + st_row;
+          stmatrix_x4(base, m[0], m[1], m[2], m[3]);        // channels +0..15
+          stmatrix_x4(base + 32, m[4], m[5], m[6], m[7]);   // channels +16..31
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {                  // 8 pixels (one image row of the block) x 64 bytes per step
+          uint4 val;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                       : "r"(rd_addr + it * 8 * C3W_EPI_PITCH));
+          if (!p.out_f32) {
+            *reinterpret_cast<uint4*>(ybase + (int64_t)it * p.W * p.ld_y + c0) = val;
+          } else {
+            const __half2* h = reinterpret_cast<const __half2*>(&val);
+            float* yr = ybase32 + (int64_t)it * p.W * p.ld_y + c0;
+            const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
+            *reinterpret_cast<float4*>(yr) = make_float4(f0.x, f0.y, f1.x, f1.y);
+            *reinterpret_cast<float4*>(yr + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+int conv3w_launch_fwd(const Conv3Call& c, Conv3Params p, cudaStream_t st) {
+  // geometry: one 16 x 16 image per CTA, halo pitch 18
+  p.pitch = 18;
+  p.a_bytes = 18u * 18u * 128u;
+  p.a_sbo = (uint32_t)(p.pitch * 128) >> 4;
+  p.idesc = (1u << 4) | ((c.b_mn ? 1u : 0u) << 16) | ((uint32_t)(C3W_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  CUtensorMap ma0, ma1, mb0, mb1;
+  const uint32_t box[4] = {64, 18, 18, 1};
+  {
+    uint64_t dims[4] = {(uint64_t)c.Ca, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a, (uint64_t)c.W * c.ld_a, (uint64_t)c.H * c.W * c.ld_a};
+    if (!make_map(&ma0, c.a, 4, dims, str, box)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[4] = {(uint64_t)c.Ca2, (uint64_t)c.W, (uint64_t)c.H, (uint64_t)c.NB};
+    uint64_t str[3] = {(uint64_t)c.ld_a2, (uint64_t)c.W * c.ld_a2, (uint64_t)c.H * c.W * c.ld_a2};
+    if (!make_map(&ma1, c.a2, 4, dims, str, box)) return BD_ERR_CUDA;
+  } else {
+    ma1 = ma0;
+  }
+  {
+    const int cols = c.b_mn ? c.N : c.Ca;
+    uint64_t dims[3] = {(uint64_t)cols, (uint64_t)c.b_rows, 9};
+    uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
+    uint32_t bbox[3] = {64, c.b_mn ? 64u : (uint32_t)C3W_BN, 1};
+    if (!make_map(&mb0, c.b, 3, dims, str, bbox)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
+    uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
+    uint32_t bbox[3] = {64, (uint32_t)C3W_BN, 1};
+    if (!make_map(&mb1, c.b2, 3, dims, str, bbox)) return BD_ERR_CUDA;
+  } else {
+    mb1 = mb0;
+  }
+  dim3 grid(c.NB, c.N / C3W_BN);
+  static bool attr_set[2] = {false, false};
+  if (c.b_mn) {
+    if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3w_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3W_SMEM); attr_set[1] = true; }
+    umma_conv3w_kernel<true><<<grid, 576, C3W_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+  } else {
+    if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3w_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3W_SMEM); attr_set[0] = true; }
+    umma_conv3w_kernel<false><<<grid, 576, C3W_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
   }
   count_launch(1);
   return BD_OK;

@@ -58,7 +58,8 @@ if what in ("all", "gn"):
               f"({4 * mb / out[1][1] / 1e3:.2f} TB/s alg)", flush=True)
 
 if what in ("all", "conv"):
-    for (B, H, Cin, Cout, res) in [(128, 32, 128, 128, False), (128, 32, 128, 128, True), (128, 32, 256, 128, True), (128, 32, 256, 256, False)]:
+    for (B, H, Cin, Cout, res) in [(128, 32, 128, 128, False), (128, 32, 128, 128, True), (128, 32, 256, 128, True), (128, 32, 256, 256, False),
+                                   (128, 16, 256, 256, False), (128, 16, 256, 256, True), (128, 16, 512, 256, False), (128, 16, 128, 256, False)]:
         x = torch.randn(B, H, H, Cin, device="cuda").half()
         w = (torch.randn(9, Cout, Cin, device="cuda") / (3 * Cin ** 0.5)).half()
         bias = torch.randn(Cout, device="cuda")
@@ -67,7 +68,7 @@ if what in ("all", "conv"):
         ys = []
         ts = []
         for old in (True, False):
-            setenv("BD_NO_CONV3P", old)
+            setenv("BD_NO_CONV3P", old); setenv("BD_NO_CONV3W", old)
             y = torch.zeros(B, H, H, Cout, dtype=torch.half, device="cuda")
             f = lambda: ops.conv_fwd(x, w, y, ksize=3, bias=bias, rowbias=rowb, residual=r, scale=0.5 if res else 1.0, impl=_lib.BD_IMPL_UMMA)
             ts.append(timed(f))
@@ -76,18 +77,18 @@ if what in ("all", "conv"):
         td = []
         dxs = []
         for old in (True, False):
-            setenv("BD_NO_CONV3P", old)
+            setenv("BD_NO_CONV3P", old); setenv("BD_NO_CONV3W", old)
             dx = torch.zeros(B, H, H, Cin, dtype=torch.half, device="cuda")
             dyy = ys[0]
             f = lambda: ops.conv_dgrad(dyy, w, dx, ksize=3, impl=_lib.BD_IMPL_UMMA)
             td.append(timed(f))
             dxs.append(dx)
-        setenv("BD_NO_CONV3P", False)
+        setenv("BD_NO_CONV3P", False); setenv("BD_NO_CONV3W", False)
         fl = 2.0 * B * H * H * Cin * Cout * 9
         err = _lib.lib().bd_umma_error()
         print(f"conv3 B={B} H={H} {Cin}->{Cout} res={res}: fwd per-tile {ts[0]:.1f} us ({fl / ts[0] / 1e6:.0f} TF/s) -> persistent "
               f"{ts[1]:.1f} us ({fl / ts[1] / 1e6:.0f} TF/s), equal={torch.equal(ys[0], ys[1])} maxdiff={float((ys[0].float() - ys[1].float()).abs().max()):.3g}; "
-              f"dgrad {td[0]:.1f} -> {td[1]:.1f} us ({fl / td[1] / 1e6:.0f} TF/s), equal={torch.equal(dxs[0], dxs[1])} umma_error={err}", flush=True)
+              f"dgrad {td[0]:.1f} -> {td[1]:.1f} us ({fl / td[1] / 1e6:.0f} TF/s), equal={torch.equal(dxs[0], dxs[1])} maxdiff={float((dxs[0].float() - dxs[1].float()).abs().max()):.3g} umma_error={err}", flush=True)
 
 if what == "gnsweep":
     G, eps = 32, 1e-6
