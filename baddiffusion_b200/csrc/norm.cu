@@ -348,6 +348,8 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
                                                               const float* __restrict__ gamma,
                                                               const float* __restrict__ beta, float* __restrict__ stats_out,
                                                               int HW, int C, int G, float eps, int apply_silu) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
   cg::cluster_group cl = cg::this_cluster();
   const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
   extern __shared__ __align__(16) unsigned char gsm[];
@@ -474,6 +476,8 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gsum, int64_t ld_gsum, int HW, int C,
     int G, int apply_silu) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
   cg::cluster_group cl = cg::this_cluster();
   const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
   extern __shared__ __align__(16) unsigned char gsm[];
@@ -682,13 +686,16 @@ static cudaError_t launch_cluster(void (*kernel)(KArgs...), dim3 grid, int threa
   cfg.blockDim = dim3(threads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = cs;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  // programmatic dependent launch: the kernels below execute griddepcontrol.wait before their first global access
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("BD_NO_PDL") ? 1 : 2;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

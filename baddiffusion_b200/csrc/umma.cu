@@ -125,6 +125,8 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -247,6 +249,8 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (nk > 0) {
     if (warp == 0) {
@@ -420,7 +424,7 @@ static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_set = true;
   }
-  kern<<<grid, 320, L::kTotal, st>>>(a0, a1, b, b1, p);
+  launch_pdl(kern, grid, dim3(320), (size_t)L::kTotal, st, a0, a1, b, b1, p);
   count_launch(1);
   return 0;
 }
@@ -583,7 +587,7 @@ static int launch_wgrad_t(const CUtensorMap& a, const CUtensorMap& b, const Wgra
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_set = true;
   }
-  kern<<<grid, 192, L::kTotal, st>>>(a, b, p);
+  launch_pdl(kern, grid, dim3(192), (size_t)L::kTotal, st, a, b, p);
   count_launch(1);
   return 0;
 }

@@ -4,6 +4,7 @@
 #include "common.cuh"
 
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace bd {
 namespace umma {
@@ -45,6 +46,13 @@ __device__ __forceinline__ bool mbar_wait(uint64_t* bar, uint32_t parity, int* e
   }
   return true;
 }
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may start
+// while its predecessor is still draining; everything before pdl_wait() (barrier init, TMEM allocation, tensor-map
+// prefetch) overlaps the predecessor's tail, everything that touches global memory comes after it.
+// launch_dependents lets the NEXT kernel's CTAs take SMs as this kernel's CTAs retire.  Both are no-ops for a
+// normally launched kernel.  Rule: every kernel launched through launch_pdl() executes pdl_wait() in all threads.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -230,6 +238,22 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
     }
   }
   __syncwarp();
+}
+
+// host: launch with the programmatic-dependent-launch attribute (BD_NO_PDL=1 -> plain launch)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("BD_NO_PDL") ? 0 : 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 // host helpers (defined in umma.cu)

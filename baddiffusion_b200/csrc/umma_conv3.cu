@@ -99,6 +99,8 @@ __global__ void __launch_bounds__(576, 1) umma_conv3_kernel(const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -349,10 +351,10 @@ int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
   if (c.b_mn) {
     if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }
-    umma_conv3_kernel<true><<<grid, 576, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    launch_pdl(umma_conv3_kernel<true>, grid, dim3(576), C3_SMEM, st, ma0, ma1, mb0, mb1, p);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
-    umma_conv3_kernel<false><<<grid, 576, C3_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    launch_pdl(umma_conv3_kernel<false>, grid, dim3(576), C3_SMEM, st, ma0, ma1, mb0, mb1, p);
   }
   count_launch(1);
   return BD_OK;
@@ -413,6 +415,8 @@ __global__ void __launch_bounds__(576, 1) umma_conv3t_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -613,6 +617,8 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     // ===== TMA producer: free-running over all tiles of this CTA =====
@@ -849,10 +855,10 @@ int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensor
     static bool pattr[2] = {false, false};
     if (a_mn) {
       if (!pattr[1]) { cudaFuncSetAttribute(umma_conv3p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[1] = true; }
-      umma_conv3p_kernel<true><<<ctas, 576, C3P_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+      launch_pdl(umma_conv3p_kernel<true>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
     } else {
       if (!pattr[0]) { cudaFuncSetAttribute(umma_conv3p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[0] = true; }
-      umma_conv3p_kernel<false><<<ctas, 576, C3P_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+      launch_pdl(umma_conv3p_kernel<false>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
     }
     count_launch(1);
     return BD_OK;
@@ -860,10 +866,10 @@ int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensor
   static bool attr_set[2] = {false, false};
   if (a_mn) {
     if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3t_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[1] = true; }
-    umma_conv3t_kernel<true><<<grid, 576, C3_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+    launch_pdl(umma_conv3t_kernel<true>, grid, dim3(576), C3_SMEM, st, mx0, mx1, mw0, mw1, p);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3t_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM); attr_set[0] = true; }
-    umma_conv3t_kernel<false><<<grid, 576, C3_SMEM, st>>>(mx0, mx1, mw0, mw1, p);
+    launch_pdl(umma_conv3t_kernel<false>, grid, dim3(576), C3_SMEM, st, mx0, mx1, mw0, mw1, p);
   }
   count_launch(1);
   return BD_OK;
@@ -939,6 +945,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3w_kernel(const __grid_consta
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
   if (threadIdx.x >= 64 && threadIdx.x < 64 + C3W_BN) {   // bias + bias2 + per-image row bias of this slab, once
+    pdl_wait();                                           // (reads global memory: not part of the overlappable prologue)
     const int c = n_tile * C3W_BN + (threadIdx.x - 64);
     float b = 0.f;
     if (p.bias) b += p.bias[c];
@@ -950,6 +957,8 @@ __global__ void __launch_bounds__(576, 1) umma_conv3w_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (warp == 0) {
     if (lane == 0) {
@@ -1131,10 +1140,10 @@ int conv3w_launch_fwd(const Conv3Call& c, Conv3Params p, cudaStream_t st) {
   static bool attr_set[2] = {false, false};
   if (c.b_mn) {
     if (!attr_set[1]) { cudaFuncSetAttribute(umma_conv3w_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3W_SMEM); attr_set[1] = true; }
-    umma_conv3w_kernel<true><<<grid, 576, C3W_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    launch_pdl(umma_conv3w_kernel<true>, grid, dim3(576), C3W_SMEM, st, ma0, ma1, mb0, mb1, p);
   } else {
     if (!attr_set[0]) { cudaFuncSetAttribute(umma_conv3w_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3W_SMEM); attr_set[0] = true; }
-    umma_conv3w_kernel<false><<<grid, 576, C3W_SMEM, st>>>(ma0, ma1, mb0, mb1, p);
+    launch_pdl(umma_conv3w_kernel<false>, grid, dim3(576), C3W_SMEM, st, ma0, ma1, mb0, mb1, p);
   }
   count_launch(1);
   return BD_OK;

@@ -64,6 +64,8 @@ __global__ void __launch_bounds__(192, 1) umma_wgrad3_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
 
   if (nk > 0) {
     if (warp == 0) {
@@ -202,7 +204,7 @@ int wgrad3_launch(const Wgrad3Call& c, cudaStream_t st) {
   }
   static bool attr_set = false;
   if (!attr_set) { cudaFuncSetAttribute(umma_wgrad3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, W3_SMEM); attr_set = true; }
-  umma_wgrad3_kernel<<<dim3(m_tiles * p.n_tiles, 3, splits), 192, W3_SMEM, st>>>(ma, mb, p);
+  launch_pdl(umma_wgrad3_kernel, dim3(m_tiles * p.n_tiles, 3, splits), dim3(192), (size_t)W3_SMEM, st, ma, mb, p);
   count_launch(1);
   return BD_OK;
 }

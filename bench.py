@@ -40,6 +40,16 @@ def peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
 
 
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel, from the committed
+    `ncu --set full` capture (profiles/roofline_kernel_traffic.json; written by scripts/ncu_traffic.py), or None."""
+    p = os.path.join(ROOT, "profiles", "roofline_kernel_traffic.json")
+    try:
+        return float(json.load(open(p))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -254,9 +264,9 @@ def run_ours(args):
         k_ms = tot / reps
         flops = 2.0 * B * H * H * C * C * 9
         achieved = flops / (k_ms / 1e3) / 1e12
-        roof = {"bound": "tensor", "kernel": "umma_conv3t_kernel (3x3 conv, halo reuse) 128->128 @32x32, B=128",
+        roof = {"bound": "tensor", "kernel": "umma_conv3p_kernel (persistent 3x3 conv, halo reuse) 128->128 @32x32, B=128",
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-                "traffic": None, "peak_source": f"{pk['src']} (burst, kernel timed alone)", "ms_per_launch": k_ms,
+                "traffic": ncu_traffic(), "peak_source": f"{pk['src']} (burst, kernel timed alone)", "ms_per_launch": k_ms,
                 "algorithmic_flops_per_launch": flops,
                 "step_tensor_frac_of_sustained": value / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sust"]}
         del x, w, y, flush
