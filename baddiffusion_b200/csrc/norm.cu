@@ -382,11 +382,19 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
       for (int k = 0; k < 8; ++k) { sq[0][k] += f[k]; sq[1][k] = fmaf(f[k], f[k], sq[1][k]); }
     }
   }
-  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {  // what the register cache does not hold
-    float f[8];
-    unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), f);
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * UNR) {  // what the register cache does not hold: UNR loads in flight
+    half8 t[UNR];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { sq[0][k] += f[k]; sq[1][k] = fmaf(f[k], f[k], sq[1][k]); }
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) t[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) {
+        float f[8];
+        unpack8(t[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sq[0][k] += f[k]; sq[1][k] = fmaf(f[k], f[k], sq[1][k]); }
+      }
   }
   gn_block_channel_sums<2>(red, chs, sq, rows, C8, C, r, v);
   // per-channel affine parameters: issued now so their latency hides behind the cluster exchange
@@ -450,15 +458,23 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
       *reinterpret_cast<half8*>(yb + (int64_t)p * ldy) = pack8(f);
     }
   }
-  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
-    float f[8];
-    unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), f);
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * UNR) {   // second read: L2-resident (this CTA read it microseconds ago)
+    half8 t[UNR];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float z = fmaf(f[k], ga[k], be[k]);
-      f[k] = apply_silu ? silu_h(z) : z;
-    }
-    *reinterpret_cast<half8*>(yb + (int64_t)p * ldy) = pack8(f);
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) t[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) {
+        float f[8];
+        unpack8(t[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float z = fmaf(f[k], ga[k], be[k]);
+          f[k] = apply_silu ? silu_h(z) : z;
+        }
+        *reinterpret_cast<half8*>(yb + (int64_t)(p + u * rows) * ldy) = pack8(f);
+      }
   }
   cl.barrier_wait();  // peers may still be reading grp[]: do not retire before they are done
 }
@@ -531,17 +547,28 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
         hd[i] = pack8(fd);   // keep dz, not dy: phase 2 does not evaluate silu' again
       }
     }
-    for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
-      float fx[8], fd[8];
-      unpack8(*reinterpret_cast<const half8*>(xb + (int64_t)p * ldx), fx);
-      unpack8(*reinterpret_cast<const half8*>(db + (int64_t)p * lddy), fd);
+    for (int p = p0 + r + VMAX * rows; p < p1; p += rows * 2) {   // 4 loads in flight
+      half8 tx[2], td[2];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float dz = fd[k];
-        if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
-        ss[0][k] += dz;
-        ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
-      }
+      for (int u = 0; u < 2; ++u)
+        if (p + u * rows < p1) {
+          tx[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+          td[u] = *reinterpret_cast<const half8*>(db + (int64_t)(p + u * rows) * lddy);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u)
+        if (p + u * rows < p1) {
+          float fx[8], fd[8];
+          unpack8(tx[u], fx);
+          unpack8(td[u], fd);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            float dz = fd[k];
+            if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+            ss[0][k] += dz;
+            ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
+          }
+        }
     }
     gn_block_channel_sums<2>(red, chs, ss, rows, C8, C, r, v);
   }
@@ -613,22 +640,35 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
       *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
     }
   }
-  for (int p = p0 + r + VMAX * rows; p < p1; p += rows) {
-    const int64_t row = rb + p;
-    float fx[8], fd[8], fa[8];
-    unpack8(*reinterpret_cast<const half8*>(x + row * ldx + v * 8), fx);
-    unpack8(*reinterpret_cast<const half8*>(dy + row * lddy + v * 8), fd);
-    if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * 2) {
+    half8 tx[2], td[2], ta[2];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      float dz = fd[k];
-      if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
-      float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
-      if (add) o += fa[k];
-      fx[k] = o;
-      so[0][k] += o;
-    }
-    *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+    for (int u = 0; u < 2; ++u)
+      if (p + u * rows < p1) {
+        const int64_t row = rb + p + u * rows;
+        tx[u] = *reinterpret_cast<const half8*>(x + row * ldx + v * 8);
+        td[u] = *reinterpret_cast<const half8*>(dy + row * lddy + v * 8);
+        if (add) ta[u] = *reinterpret_cast<const half8*>(add + row * ldadd + v * 8);
+      }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (p + u * rows < p1) {
+        const int64_t row = rb + p + u * rows;
+        float fx[8], fd[8], fa[8];
+        unpack8(tx[u], fx);
+        unpack8(td[u], fd);
+        if (add) unpack8(ta[u], fa);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float dz = fd[k];
+          if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+          float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
+          if (add) o += fa[k];
+          fx[k] = o;
+          so[0][k] += o;
+        }
+        *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+      }
   }
   cl.barrier_wait();  // every CTA has finished reading chs[]
   if (gsum) {         // uniform across the cluster
