@@ -353,25 +353,53 @@ __global__ void __launch_bounds__(256) temb_mlp_kernel(const int64_t* __restrict
   if (sin_out)
     for (int i = threadIdx.x; i < dim; i += blockDim.x) sin_out[(int64_t)b * dim + i] = se[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int n = warp; n < temb; n += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < dim; k += 32) acc = fmaf(w1[(int64_t)n * dim + k], se[k], acc);
-    acc = warp_sum(acc);
+  // A warp owns 4 output rows at a time: 4 independent dot products keep 4x the loads in flight (the kernel is a
+  // chain of L2 round trips, not arithmetic).  Per-row accumulation order is unchanged (lane-strided k, then the
+  // shuffle tree), so results are bit-identical to the one-row-at-a-time form.
+  constexpr int R = 4;
+  for (int n0 = warp * R; n0 < temb; n0 += nw * R) {
+    float acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0.f;
+    for (int k = lane; k < dim; k += 32) {
+      const float sv = se[k];
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (n0 + j < temb) acc[j] = fmaf(w1[(int64_t)(n0 + j) * dim + k], sv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = warp_sum(acc[j]);
     if (lane == 0) {
-      float h = acc + b1[n];
-      if (h1) h1[(int64_t)b * temb + n] = h;
-      sa[n] = silu_f(h);
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (n0 + j < temb) {
+          float h = acc[j] + b1[n0 + j];
+          if (h1) h1[(int64_t)b * temb + n0 + j] = h;
+          sa[n0 + j] = silu_f(h);
+        }
     }
   }
   __syncthreads();
-  for (int n = warp; n < temb; n += nw) {
-    float acc = 0.f;
-    for (int k = lane; k < temb; k += 32) acc = fmaf(w2[(int64_t)n * temb + k], sa[k], acc);
-    acc = warp_sum(acc);
+  for (int n0 = warp * R; n0 < temb; n0 += nw * R) {
+    float acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0.f;
+    for (int k = lane; k < temb; k += 32) {
+      const float sv = sa[k];
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (n0 + j < temb) acc[j] = fmaf(w2[(int64_t)(n0 + j) * temb + k], sv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = warp_sum(acc[j]);
     if (lane == 0) {
-      float e = acc + b2[n];
-      emb[(int64_t)b * temb + n] = e;
-      if (silu_emb) silu_emb[(int64_t)b * temb + n] = __float2half_rn(silu_f(e));
+#pragma unroll
+      for (int j = 0; j < R; ++j)
+        if (n0 + j < temb) {
+          float e = acc[j] + b2[n0 + j];
+          emb[(int64_t)b * temb + n0 + j] = e;
+          if (silu_emb) silu_emb[(int64_t)b * temb + n0 + j] = __float2half_rn(silu_f(e));
+        }
     }
   }
 }

@@ -33,6 +33,7 @@ struct FpropParams {
   int nseg;
   KSeg seg[kMaxSeg];
   int total_kblocks;
+  int splits;            // split-K factor = cluster size along z (1: none)
   int tiles_w, tiles_h;  // tiles per image
   int bw, bh, bn;        // pixel box (product 128)
   int W, H, NB;          // image geometry
@@ -127,18 +128,22 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
+  // split-K: rank r of the (1,1,S) cluster owns k-blocks [it_begin, it_end) of the flattened segment list
+  const int S = p.splits, rank = S > 1 ? (int)cluster_ctarank() : 0;
+  const int it_begin = (int)((long long)p.total_kblocks * rank / S), it_end = (int)((long long)p.total_kblocks * (rank + 1) / S);
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      int stage = 0;
+      int stage = 0, it = 0;
       uint32_t phase = 0;
       bool ok = true;
       for (int s = 0; s < p.nseg && ok; ++s) {
         const KSeg sg = p.seg[s];
         const CUtensorMap* mapA = sg.a_src ? &tmA1 : &tmA0;
         const CUtensorMap* mapB = sg.b_src ? &tmB1 : &tmB0;
-        for (int kb = 0; kb < sg.nblk; ++kb) {
+        for (int kb = 0; kb < sg.nblk; ++kb, ++it) {
+          if (it < it_begin || it >= it_end) continue;   // another rank of the split-K cluster owns this k-block
           ok = mbar_wait(&empty[stage], phase ^ 1, p.error_flag, 1);
           if (!ok) break;
           uint8_t* sa = smem + stage * L::kStageBytes;
@@ -163,7 +168,7 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
-      for (int it = 0; it < p.total_kblocks; ++it) {
+      for (int it = it_begin; it < it_end; ++it) {
         ok = mbar_wait(&full[stage], phase, p.error_flag, 2);
         if (!ok) break;
         tc_fence_after();
@@ -174,7 +179,7 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
           // K-major: advance 16 elements = 32 B inside the 128B swizzle row; MN-major: 16 k-rows = 2048 B
           const uint64_t ad = make_desc(sa + k * 32 + p.dbg_shift * 128, p.a_lbo, p.a_sbo) | ((uint64_t)(p.dbg_boff & 7) << 49);
           const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
-          umma_f16(tmem_base, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_f16(tmem_base, ad, bd, p.idesc, (it > it_begin || k > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
         if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -193,12 +198,22 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
     const int64_t m = (int64_t)n * p.out_sn + h * p.out_sh + w * p.out_sw + p.out_off;  // output / residual pixel
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
     tc_fence_after();
-    if (ok) {
-      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (BN / 2 + 4);  // operand stages are free now
-      EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
-      epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
-                            n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (BN / 2 + 4);  // operand stages are free now
+    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+    if (S == 1) {
+      if (ok)
+        epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
+                              n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+    } else {
+      if (ok) epilogue_stage_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane);
+      cluster_sync_all();   // every rank's partial tile is staged (all threads of the cluster take part, see below)
+      epilogue_splitk_finish_warp<BN / 2>(stage, lane, S, rank, m, mlin, valid, n_tile * BN + half * (BN / 2), e, p.rowbias,
+                                          p.ld_rowbias, p.HW);
     }
+  }
+  if (S > 1) {
+    if (warp < 2) cluster_sync_all();   // producer / MMA warps: the barrier the epilogue warps passed after staging
+    cluster_sync_all();                 // no CTA retires while a peer still reads its staging tile
   }
   tc_fence_before();
   __syncthreads();
@@ -424,7 +439,25 @@ static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_set = true;
   }
-  launch_pdl(kern, grid, dim3(320), (size_t)L::kTotal, st, a0, a1, b, b1, p);
+  if (p.splits > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(320);
+    cfg.dynamicSmemBytes = (size_t)L::kTotal;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = p.splits;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("BD_NO_PDL") ? 1 : 2;
+    cudaLaunchKernelEx(&cfg, kern, a0, a1, b, b1, p);
+  } else {
+    launch_pdl(kern, grid, dim3(320), (size_t)L::kTotal, st, a0, a1, b, b1, p);
+  }
   count_launch(1);
   return 0;
 }
@@ -547,7 +580,14 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
     mb1 = mb;
   }
   const int m_tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.bn);
-  dim3 grid(m_tiles, c.N / BN);
+  // split-K (cluster of S CTAs per output tile) when the tile grid leaves most SMs idle and K is long: the 3x3 convs
+  // of the 8x8 / 4x4 levels (128 / 32 tiles, 36-72 k-blocks each)
+  p.splits = 1;
+  if (!getenv("BD_NO_SPLITK")) {
+    const int tiles = m_tiles * (c.N / BN);
+    while (p.splits < 4 && tiles * p.splits * 2 <= 2 * num_sms() && p.total_kblocks / (p.splits * 2) >= 6) p.splits *= 2;
+  }
+  dim3 grid(m_tiles, c.N / BN, p.splits);
   if (BN == 128) {
     if (c.b_mn) launch_fprop_t<128, true>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false>(ma0, ma1, mb, mb1, p, grid, st);
   } else {

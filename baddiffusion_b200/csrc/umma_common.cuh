@@ -256,6 +256,98 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Split-K inside a thread-block cluster: the S CTAs of a cluster (cluster dims (1,1,S)) accumulate disjoint k-block
+// ranges of the SAME output tile.  Each stages its fp32 partial tile in its own shared memory (phase 1), the cluster
+// meets at a barrier, and rank r finishes every S-th group of rows: it adds the S partials in rank order through
+// distributed shared memory (deterministic), applies the usual epilogue and writes the result (phase 2).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float4 ld_dsmem_f4(uint32_t local_smem_addr, uint32_t rank) {
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(local_smem_addr), "r"(rank));
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(ra) : "memory");
+  return v;
+}
+
+// phase 1: TMEM -> this warp's fp32 staging tile [32 rows][CW + 4]
+template <int CW>
+__device__ __forceinline__ void epilogue_stage_warp(uint32_t taddr, float* __restrict__ stage, int lane) {
+  constexpr int PITCH = CW + 4;
+  float* myrow = stage + lane * PITCH;
+#pragma unroll
+  for (int c0 = 0; c0 < CW; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(taddr + c0, v);
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      *reinterpret_cast<float4*>(myrow + c0 + j) =
+          make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+  }
+}
+
+// phase 2 (after the cluster barrier): rows r0 = RPI * i with i % S == rank
+template <int CW>
+__device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restrict__ stage, int lane, int S, int rank,
+                                                            int64_t m_own, int64_t mlin_own, bool valid_own, int col0,
+                                                            const EpiArgs& e, const float* __restrict__ rowbias,
+                                                            int64_t ld_rowbias, int HW) {
+  constexpr int PITCH = CW + 4;
+  constexpr int LPR = CW / 8;
+  constexpr int RPI = 32 / LPR;
+  const int piece = lane % LPR, rsub = lane / LPR;
+  const int col = col0 + piece * 8;
+  float bsum[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (e.bias) {
+    const float4 a = *reinterpret_cast<const float4*>(e.bias + col), b = *reinterpret_cast<const float4*>(e.bias + col + 4);
+    bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w; bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
+  }
+  if (e.bias2) {
+    const float4 a = *reinterpret_cast<const float4*>(e.bias2 + col), b = *reinterpret_cast<const float4*>(e.bias2 + col + 4);
+    bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w; bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
+  }
+  for (int it = rank; it < 32 / RPI; it += S) {
+    const int row = it * RPI + rsub;
+    const int64_t m = __shfl_sync(0xffffffffu, m_own, row);
+    const int64_t mlin = __shfl_sync(0xffffffffu, mlin_own, row);
+    const int valid = __shfl_sync(0xffffffffu, (int)valid_own, row);
+    if (!valid) continue;
+    const uint32_t sp = smem_u32(stage + row * PITCH + piece * 8);
+    float f[8] = {bsum[0], bsum[1], bsum[2], bsum[3], bsum[4], bsum[5], bsum[6], bsum[7]};
+    for (int rk = 0; rk < S; ++rk) {
+      const float4 a = ld_dsmem_f4(sp, rk), b = ld_dsmem_f4(sp + 16, rk);
+      f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
+    }
+    if (rowbias) {
+      const float* rb = rowbias + (mlin / HW) * ld_rowbias + col;
+      const float4 ra = *reinterpret_cast<const float4*>(rb), rc = *reinterpret_cast<const float4*>(rb + 4);
+      f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w; f[4] += rc.x; f[5] += rc.y; f[6] += rc.z; f[7] += rc.w;
+    }
+    if (e.residual) {
+      float g[8];
+      unpack8(*reinterpret_cast<const half8*>(e.residual + m * e.ld_res + col), g);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] += g[k];
+    }
+    if (e.scale != 1.0f) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) f[k] *= e.scale;
+    }
+    if (e.out_f32) {
+      float* yr = reinterpret_cast<float*>(e.y) + m * e.ld_y + col;
+      *reinterpret_cast<float4*>(yr) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(yr + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    } else {
+      *reinterpret_cast<half8*>(reinterpret_cast<__half*>(e.y) + m * e.ld_y + col) = pack8(f);
+    }
+  }
+}
+
 // host helpers (defined in umma.cu)
 bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_elems,
               const uint32_t* box, const uint32_t* elem_strides = nullptr);
