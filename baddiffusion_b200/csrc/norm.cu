@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
   const int p0 = (int)((int64_t)HW * rank / CS), p1 = (int)((int64_t)HW * (rank + 1) / CS);
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
   __half* yb = y + (int64_t)b * HW * ldy + v * 8;
-  half8 hv[VMAX];
+  half8 hv[VMAX > 0 ? VMAX : 1];
   float sq[2][8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) sq[0][k] = sq[1][k] = 0.f;
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
 // (D/models/resnet.py:574-580), which otherwise cost one extra pass over dx each.
 // dynamic smem: red[threads][16] f32 | chs[2][C] f32 | chs2[C] f32 | tot[2][C] f32 | gab[G][2] f32
 template <int VMAX>
-__global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
+__global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
     const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
@@ -509,7 +509,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
   const int64_t rb = (int64_t)b * HW;
   const __half* xb = x + rb * ldx + v * 8;
   const __half* db = dy + rb * lddy + v * 8;
-  half8 hx[VMAX], hd[VMAX];
+  half8 hx[VMAX > 0 ? VMAX : 1], hd[VMAX > 0 ? VMAX : 1];
 #pragma unroll
   for (int i = 0; i < VMAX; ++i) {
     const int p = p0 + r + i * rows;
@@ -547,16 +547,17 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
         hd[i] = pack8(fd);   // keep dz, not dy: phase 2 does not evaluate silu' again
       }
     }
-    for (int p = p0 + r + VMAX * rows; p < p1; p += rows * 2) {   // 4 loads in flight
-      half8 tx[2], td[2];
+    constexpr int TU = VMAX == 0 ? 4 : 2;   // 2*TU loads in flight
+    for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU) {
+      half8 tx[TU], td[TU];
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < TU; ++u)
         if (p + u * rows < p1) {
           tx[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
           td[u] = *reinterpret_cast<const half8*>(db + (int64_t)(p + u * rows) * lddy);
         }
 #pragma unroll
-      for (int u = 0; u < 2; ++u)
+      for (int u = 0; u < TU; ++u)
         if (p + u * rows < p1) {
           float fx[8], fd[8];
           unpack8(tx[u], fx);
@@ -640,10 +641,11 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
       *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
     }
   }
-  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * 2) {
-    half8 tx[2], td[2], ta[2];
+  constexpr int TU2 = VMAX == 0 ? 3 : 2;
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU2) {
+    half8 tx[TU2], td[TU2], ta[TU2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < TU2; ++u)
       if (p + u * rows < p1) {
         const int64_t row = rb + p + u * rows;
         tx[u] = *reinterpret_cast<const half8*>(x + row * ldx + v * 8);
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(256, 2) gn_bwd_fused_kernel(
         if (add) ta[u] = *reinterpret_cast<const half8*>(add + row * ldadd + v * 8);
       }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < TU2; ++u)
       if (p + u * rows < p1) {
         const int64_t row = rb + p + u * rows;
         float fx[8], fd[8], fa[8];
@@ -770,7 +772,8 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
     if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_FT", 256), vmax, &fthreads, &cs) &&
         (size_t)fthreads * 64 >= (size_t)cs * 2 * G * sizeof(double)) {   // red[] doubles as the peer-partials gather buffer
       const size_t smem = (size_t)fthreads * 64 + (size_t)2 * C * 4 + (size_t)2 * G * 8 + (size_t)2 * G * 4;
-      cudaError_t e = launch_cluster(vmax == 4 ? gn_fwd_fused_kernel<4> : gn_fwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
+      const bool stream_fwd = gn_env_int("BD_GN_FWD_STREAM", 0) != 0;
+      cudaError_t e = launch_cluster(stream_fwd ? gn_fwd_fused_kernel<0> : vmax == 4 ? gn_fwd_fused_kernel<4> : gn_fwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, stats,
                                      HW, C, G, eps, apply_silu);
       if (e != cudaSuccess) { set_error("bd_groupnorm_fwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
@@ -807,7 +810,8 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
     const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;
     if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs)) {
       const size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
-      cudaError_t e = launch_cluster(vmax == 4 ? gn_bwd_fused_kernel<4> : gn_bwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
+      const bool stream_bwd = gn_env_int("BD_GN_BWD_STREAM", 0) != 0;
+      cudaError_t e = launch_cluster(stream_bwd ? gn_bwd_fused_kernel<0> : vmax == 4 ? gn_bwd_fused_kernel<4> : gn_bwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
                                      (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
                                      gsum, ld_gsum, HW, C, G, apply_silu);

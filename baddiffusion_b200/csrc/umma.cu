@@ -324,9 +324,12 @@ __global__ void __launch_bounds__(192, 2) umma_wgrad_kernel(const __grid_constan
           if (row < p.Mtot && col < p.Ntot) {
             const int64_t off = ((int64_t)z * p.Mtot + row) * p.ld_y + col;
             if (p.out_mode == 0) {
-              float* yr = reinterpret_cast<float*>(p.y) + off;
+              float* yr = reinterpret_cast<float*>(p.y) + off;   // 16-byte aligned: ld_y and col are multiples of 32
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(yr + j, __uint_as_float(v[j]));
+              for (int j = 0; j < 32; j += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(yr + j), "f"(__uint_as_float(v[j])),
+                             "f"(__uint_as_float(v[j + 1])), "f"(__uint_as_float(v[j + 2])), "f"(__uint_as_float(v[j + 3]))
+                             : "memory");
             } else if (p.out_mode == 1) {
               float* yr = reinterpret_cast<float*>(p.y) + off;
 #pragma unroll

@@ -318,6 +318,49 @@ def test_conv_wgrad(ops, impl, B, H, Cin, Cout, k):
     assert rel_err(dw, 2 * refp) < 2e-3
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(80, 32, 128, 128),   # 160 tiles on 148 persistent CTAs: a CTA walks 2 tiles
+                                          (40, 32, 256, 256),   # two 128-channel slabs, 4 k-blocks
+                                          (37, 16, 256, 256),   # 16x16: one image x 256 channels per CTA, odd batch
+                                          (9, 16, 128, 512),    # two 256-channel slabs; dgrad falls back (N = 128)
+                                          (128, 4, 256, 256),   # split-K cluster of 4 (32 tiles)
+                                          (128, 8, 512, 256)])  # split-K cluster of 2 (128 tiles), 72 k-blocks
+def test_conv3_bench_sized_kernels(ops, B, H, Cin, Cout):
+    """The persistent 32x32 kernel (conv3p), the 256-wide 16x16 kernel (conv3w) and the split-K cluster path of the
+    generic kernel at the bench's per-GPU sizes: forward (bias + per-sample row bias + residual through the identity
+    K-segment + scale), the fused 1x1 shortcut segment, dgrad, all against torch fp32 on the same fp16 inputs."""
+    im = ops.L.BD_IMPL_UMMA
+    x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, 3, seed=3)
+    bias = torch.randn(Cout, device="cuda")
+    rowbias = torch.randn(B, Cout, device="cuda")
+    res, resr = nhwc_half(torch.randn(B, Cout, H, H, device="cuda"))
+    y = torch.empty(B, H, H, Cout, dtype=torch.half, device="cuda")
+    ops.conv_fwd(x, w, y, ksize=3, bias=bias, rowbias=rowbias, residual=res, scale=0.5, impl=im)
+    assert ops.umma_error() == 0
+    ref = (F.conv2d(xr, wr, bias, padding=1) + rowbias[:, :, None, None] + resr) * 0.5
+    assert (to_nchw(y) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+    # run-to-run bitwise reproducibility (fixed reduction orders, no atomics in forward / dgrad)
+    y2 = torch.empty_like(y)
+    ops.conv_fwd(x, w, y2, ksize=3, bias=bias, rowbias=rowbias, residual=res, scale=0.5, impl=im)
+    assert torch.equal(y, y2)
+    # fused 1x1 shortcut over a second input
+    C2 = 128
+    x2, x2r = nhwc_half(torch.randn(B, C2, H, H, device="cuda"))
+    ws, wsr = packed(torch.randn(Cout, C2, 1, 1, device="cuda") / math.sqrt(C2))
+    b2 = torch.randn(Cout, device="cuda")
+    ops.conv_fwd(x, w, y, ksize=3, bias=bias, bias2=b2, x2=x2, w2=ws, impl=im)
+    assert ops.umma_error() == 0
+    ref = F.conv2d(xr, wr, bias, padding=1) + F.conv2d(x2r, wsr, b2)
+    assert (to_nchw(y) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+    # dgrad (MN-major view of the same weights)
+    dy, dyr = nhwc_half(torch.randn(B, Cout, H, H, device="cuda"))
+    add, addr = nhwc_half(torch.randn(B, Cin, H, H, device="cuda"))
+    dx = torch.empty(B, H, H, Cin, dtype=torch.half, device="cuda")
+    ops.conv_dgrad(dy, w, dx, ksize=3, residual=add, impl=im)
+    assert ops.umma_error() == 0
+    ref = torch.nn.grad.conv2d_input(xr.shape, wr, dyr, padding=1) + addr
+    assert (to_nchw(dx) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+
+
 @pytest.mark.parametrize("impl", ["simt", "umma"])
 @pytest.mark.parametrize("pad,B,H,Cc", [(0, 3, 16, 128), (1, 3, 16, 128), (0, 2, 32, 128), (0, 5, 8, 256)])
 def test_conv_stride2(ops, impl, pad, B, H, Cc):
