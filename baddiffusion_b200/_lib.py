@@ -54,7 +54,7 @@ _SIGS = {
     "bd_sgemm": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_gn_workspace_floats": (sz, [i32, i32]),
     "bd_groupnorm_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
-    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_dgrad": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_wgrad": (i32, [vp, i64, vp, i64, vp, vp] + [i32] * 10 + [vp]),

@@ -228,7 +228,8 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
 // smem: cs[2][C]
 __global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restrict__ work, const float* __restrict__ gamma,
                                                            float* __restrict__ gab, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, int HW, int C, int G, int splits) {
+                                                           float* __restrict__ dbeta, float* __restrict__ dgb_parts, int HW,
+                                                           int C, int G, int splits) {
   extern __shared__ float cs[];
   const int b = blockIdx.x, cpg = C / G;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -240,8 +241,13 @@ __global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restri
     }
     cs[c] = s1;
     cs[C + c] = s2;
-    atomicAdd(dbeta + c, s1);
-    atomicAdd(dgamma + c, s2);
+    if (dgb_parts) {
+      dgb_parts[(int64_t)b * 2 * C + c] = s1;
+      dgb_parts[(int64_t)b * 2 * C + C + c] = s2;
+    } else {
+      atomicAdd(dbeta + c, s1);
+      atomicAdd(dgamma + c, s2);
+    }
   }
   __syncthreads();
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
@@ -490,8 +496,8 @@ __global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
     const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ gsum, int64_t ld_gsum, int HW, int C,
-    int G, int apply_silu) {
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dgb_parts, float* __restrict__ gsum,
+    int64_t ld_gsum, int HW, int C, int G, int apply_silu) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
   cg::cluster_group cl = cg::this_cluster();
@@ -594,8 +600,13 @@ __global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
     tot[ch] = sa;
     tot[C + ch] = sq;
     if (rank == 0) {
-      atomicAdd(dbeta + ch, sa);
-      atomicAdd(dgamma + ch, sq);
+      if (dgb_parts) {   // per-sample partials, summed over the batch by bd_bias_from_gsum (no atomics, fixed order)
+        dgb_parts[(int64_t)b * 2 * C + ch] = sa;
+        dgb_parts[(int64_t)b * 2 * C + C + ch] = sq;
+      } else {
+        atomicAdd(dbeta + ch, sa);
+        atomicAdd(dgamma + ch, sq);
+      }
     }
   }
   cl.barrier_arrive();
@@ -798,9 +809,9 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
 
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
-                     float* dbeta, float* work, float* gsum, int64_t ld_gsum, int B, int HW, int C, int G, int apply_silu,
-                     void* stream) {
-  BD_CHECK_ARG(x && dy && dx && gamma && beta && stats && dgamma && dbeta && work, "bd_groupnorm_bwd: null pointer");
+                     float* dbeta, float* work, float* gsum, int64_t ld_gsum, float* dgb_parts, int B, int HW, int C, int G,
+                     int apply_silu, void* stream) {
+  BD_CHECK_ARG(x && dy && dx && gamma && beta && stats && work && (dgb_parts || (dgamma && dbeta)), "bd_groupnorm_bwd: null pointer");
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && C <= 2048 &&
                    (!add_dx || ld_add % 8 == 0),
                "bd_groupnorm_bwd: bad shape (C=%d G=%d)", C, G);
@@ -814,7 +825,7 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
       cudaError_t e = launch_cluster(stream_bwd ? gn_bwd_fused_kernel<0> : vmax == 4 ? gn_bwd_fused_kernel<4> : gn_bwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
                                      (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
-                                     gsum, ld_gsum, HW, C, G, apply_silu);
+                                     dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu);
       if (e != cudaSuccess) { set_error("bd_groupnorm_bwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
       count_launch(1);
       BD_CHECK_LAUNCH();
@@ -827,7 +838,7 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu);
   // group sums live right behind the per-split partials in the workspace
   float* gab = work + (size_t)B * splits * 2 * C;
-  gn_bwd_group_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(work, gamma, gab, dgamma, dbeta, HW, C, G, splits);
+  gn_bwd_group_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(work, gamma, gab, dgamma, dbeta, dgb_parts, HW, C, G, splits);
   gn_bwd_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
       stats, gab, HW, C, G, asplits, apply_silu);

@@ -60,6 +60,7 @@ class UNetEngine:
         self._pool: Dict[tuple, torch.Tensor] = {}
         self.io: Dict[str, torch.Tensor] = {}
         self._bias_jobs: List[tuple] = []   # (gs view, bias-gradient view): one batched launch at the end of backward
+        self._gn_parts: Dict[int, torch.Tensor] = {}
         self.named: Dict[str, Act] = {}  # layer prefix -> output (introspection / parity debugging)
         self.flat16 = model.flat_half()
         self.flat32 = model.flat_params
@@ -111,6 +112,26 @@ class UNetEngine:
             a.g = self.new(H, C)
             a.gs = torch.empty(self.B, C, device=self.dev)
         return a
+
+    def _gn_bwd(self, x, dy, dx, gamma, beta, stats, dgamma, dbeta, silu, add_dx=None, gsum=None):
+        """GroupNorm backward whose dgamma / dbeta leave as per-sample partials (B, 2C) and are summed over the batch by
+        the batched column-sum launch at the end of backward (no atomics: 128 samples x 2C same-address updates per
+        layer otherwise)."""
+        if os.environ.get("BD_GN_ATOMIC_DGB"):
+            ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, self.gn_work, self.G, silu, add_dx=add_dx, gsum=gsum)
+            return
+        ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, self.gn_work, self.G, silu, add_dx=add_dx, gsum=gsum,
+                          parts=self._gn_parts[dgamma.data_ptr()])
+
+    def _reg_gn(self, dgamma, dbeta):
+        """Plan-build time: the per-sample {dbeta | dgamma} buffer of one GroupNorm and its two batch-sum jobs."""
+        if os.environ.get("BD_GN_ATOMIC_DGB"):
+            return
+        Cc = dgamma.numel()
+        parts = torch.empty(self.B, 2 * Cc, device=self.dev)
+        self._gn_parts[dgamma.data_ptr()] = parts
+        self._bias_jobs.append((parts[:, :Cc], dbeta))
+        self._bias_jobs.append((parts[:, Cc:], dgamma))
 
     def _bias_from(self, out: Act, *grads):
         """Bias gradients of the layer that produced `out`: from out.gs when the last writer of out.g left the channel
@@ -324,6 +345,8 @@ class UNetEngine:
         def emit():
             g = {s: self.G32(p + s) for s in ("norm1.weight", "norm1.bias", "conv1.weight", "conv1.bias", "norm2.weight",
                                               "norm2.bias", "conv2.weight", "conv2.bias")}
+            self._reg_gn(g["norm1.weight"], g["norm1.bias"])
+            self._reg_gn(g["norm2.weight"], g["norm2.bias"])
             gws = self.G32(p + "conv_shortcut.weight") if has_sc else None
             gbs = self.G32(p + "conv_shortcut.bias") if has_sc else None
             d_a2 = self.scratch(H, Cout, "da2")
@@ -352,18 +375,18 @@ class UNetEngine:
                 self._fork(wg2)
                 ops.conv_dgrad(dout, w2, d_a2, ksize=3, impl=impl)
                 # gsum = per-sample channel sums of d_h1 = gradient of the temb projection (resnet.py:577-580 broadcast add)
-                ops.groupnorm_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], gw, G, True, gsum=dcol)
+                self._gn_bwd(h1, d_a2, d_h1, n2w, n2b, st2, g["norm2.weight"], g["norm2.bias"], True, gsum=dcol)
                 self._fork(wg1)
                 ops.conv_dgrad(d_h1, w1, d_a1, ksize=3, impl=impl)
                 # input gradient: residual / shortcut branch + norm1 branch (+ whatever is already there)
                 if has_sc:
                     ops.conv_dgrad(dout, ws, x.g, ksize=1, residual=x.g if x_filled else None, impl=impl)
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g, gsum=xgs)
+                    self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=x.g, gsum=xgs)
                 elif x_filled:
                     ops.add_f16(x.g, dout, x.g)
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=x.g, gsum=xgs)
+                    self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=x.g, gsum=xgs)
                 else:
-                    ops.groupnorm_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], gw, G, True, add_dx=dout, gsum=xgs)
+                    self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=dout, gsum=xgs)
 
             self.bwd.append(bw)
             x.g_filled = True
@@ -414,6 +437,7 @@ class UNetEngine:
 
         def emit():
             g_gnw, g_gnb = self.G32(p + "group_norm.weight"), self.G32(p + "group_norm.bias")
+            self._reg_gn(g_gnw, g_gnb)
             g_wqkv = self.gflat[off: off + 3 * C * C].view(1, 3 * C, C)
             g_bqkv = self.gflat[boff: boff + 3 * C]
             g_wp, g_bp = self.G32(p + "proj_attn.weight").view(1, C, C), self.G32(p + "proj_attn.bias")
@@ -434,9 +458,9 @@ class UNetEngine:
                 ops.conv_dgrad(d_qkv, wqkv, d_a, ksize=1, impl=impl)
                 if x_filled:
                     ops.add_f16(x.g, dout, x.g)
-                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=x.g, gsum=xgs)
+                    self._gn_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, False, add_dx=x.g, gsum=xgs)
                 else:
-                    ops.groupnorm_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, gw, G, False, add_dx=dout, gsum=xgs)
+                    self._gn_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, False, add_dx=dout, gsum=xgs)
 
             self.bwd.append(bw)
             x.g_filled = True
@@ -526,13 +550,14 @@ class UNetEngine:
 
         def emit():
             g_nw, g_nb = self.G32("conv_norm_out.weight"), self.G32("conv_norm_out.bias")
+            self._reg_gn(g_nw, g_nb)
             g_w, g_b = self.G32("conv_out.weight"), self.G32("conv_out.bias")
             d_a = self.scratch(H, C, "dco")
             assert not x.g_filled
 
             def bw():
                 ops.conv_out_bwd(a, w, self.io["d_eps"], d_a, g_w, g_b, accumulate=True)
-                ops.groupnorm_bwd(x.t, d_a, x.g, nw, nb, st, g_nw, g_nb, gw, G, True, gsum=x.gs)
+                self._gn_bwd(x.t, d_a, x.g, nw, nb, st, g_nw, g_nb, True, gsum=x.gs)
 
             self.bwd.append(bw)
             x.g_filled = True

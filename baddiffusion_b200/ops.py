@@ -102,8 +102,10 @@ def groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, silu):
                                    float(eps), int(silu), _s()))
 
 
-def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None):
-    """gsum: optional (B, C) f32 view (row stride free) that receives the per-sample channel sums of dx."""
+def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None, parts=None):
+    """gsum: optional (B, C) f32 view (row stride free) that receives the per-sample channel sums of dx.
+    parts: optional contiguous (B, 2C) f32 that receives the per-sample {dbeta | dgamma} terms instead of the atomic
+    accumulation into dgamma / dbeta (sum over the batch with bias_from_gsum)."""
     px, ldx, B, H, W, Cc = _view(x)
     pdy, lddy, *_ = _view(dy)
     pdx, lddx, *_ = _view(dx)
@@ -114,8 +116,10 @@ def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, a
     if gsum is not None:
         assert gsum.dtype == torch.float32 and gsum.shape == (B, Cc) and gsum.stride(1) == 1
         pg, ldg = gsum.data_ptr(), gsum.stride(0)
+    if parts is not None:
+        assert parts.dtype == torch.float32 and parts.shape == (B, 2 * Cc) and parts.is_contiguous()
     check(L.lib().bd_groupnorm_bwd(px, ldx, pdy, lddy, pa, lda, pdx, lddx, _p(gamma), _p(beta), _p(stats), _p(dgamma),
-                                   _p(dbeta), _p(work), pg, ldg, B, H * W, Cc, G, int(silu), _s()))
+                                   _p(dbeta), _p(work), pg, ldg, _p(parts), B, H * W, Cc, G, int(silu), _s()))
 
 
 def _conv_args(x, w, y, Cin, Cout, ksize, mode, pad, bias, bias2, rowbias, residual, x2, w2, scale, impl, geom=None):

@@ -116,7 +116,11 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
                      float* dbeta, float* dgb_work,
                      float* gsum /* nullable: (B, C) f32 with row stride ld_gsum, OVERWRITTEN with the per-sample
                                     channel sums of dx = the bias / time_emb_proj gradient of x's producer */,
-                     int64_t ld_gsum, int B, int HW, int C, int G, int apply_silu, void* stream);
+                     int64_t ld_gsum,
+                     float* dgb_parts /* nullable: (B, 2C) f32, OVERWRITTEN with this sample's {dbeta | dgamma} terms
+                                         instead of atomically accumulating into dgamma / dbeta (which may then be
+                                         null); the caller sums over the batch with bd_bias_from_gsum */,
+                     int B, int HW, int C, int G, int apply_silu, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K1/K2/K3/K6/K9/K10  convolution / linear as (implicit) GEMM on fp16 NHWC views, fp32 accumulate.

@@ -184,6 +184,12 @@ def test_groupnorm_fwd_bwd(ops, B, C, H, silu):
     ref_sum = (xr.grad + addr).sum(dim=(2, 3))
     assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05
     assert bool((gsum_wide[:, C:] == 7.0).all())
+    # per-sample {dbeta | dgamma} partials instead of atomics: identical dx, batch sums equal the gradients
+    parts = torch.empty(B, 2 * C, device="cuda")
+    dx2 = torch.empty_like(x)
+    ops.groupnorm_bwd(x, dy, dx2, gamma, beta, stats, None, None, work, G, silu, add_dx=add, parts=parts)
+    assert torch.equal(dx, dx2)
+    assert rel_err(parts[:, C:].sum(0), gr.grad) < 2e-3 and rel_err(parts[:, :C].sum(0), br.grad) < 2e-3
 
 
 @pytest.mark.parametrize("B,C,H", [(128, 128, 32), (128, 256, 16), (128, 384, 32), (130, 512, 8), (4, 128, 64), (2, 128, 256)])
