@@ -431,10 +431,12 @@ static bool pick_box(int H, int W, int pixels, int* bw, int* bh, int* bn) {
   return *bw <= 256 && *bh <= 256 && *bn <= 256;
 }
 
-template <int BN, bool B_MN>
+// kStages = 3 (3 x 32 KB): two CTAs per SM, so one drains its accumulator while the other streams operands -- for grids
+// with more CTAs than SMs.  kStages = 6: grids that put at most one CTA on an SM anyway (the 8x8 / 4x4 levels) are a
+// chain of TMA round trips (a k-block's MMAs take 256 cycles, a stage refill ~1 us): twice the loads in flight.
+template <int BN, bool B_MN, int kStages>
 static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
                           const FpropParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one drains its accumulator while the other streams operands
   using L = Smem<BN, kStages>;
   auto kern = umma_fprop_kernel<BN, kStages, B_MN>;
   static bool attr_set = false;
@@ -588,13 +590,19 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   p.splits = 1;
   if (!getenv("BD_NO_SPLITK")) {
     const int tiles = m_tiles * (c.N / BN);
-    while (p.splits < 4 && tiles * p.splits * 2 <= 2 * num_sms() && p.total_kblocks / (p.splits * 2) >= 6) p.splits *= 2;
+    const int budget = (int)env_u32("BD_SPLITK_CTAS", num_sms());   // stay at one CTA per SM: the 6-stage ring below
+    while (p.splits < 4 && tiles * p.splits * 2 <= budget && p.total_kblocks / (p.splits * 2) >= 6) p.splits *= 2;
   }
   dim3 grid(m_tiles, c.N / BN, p.splits);
+  const bool deep = (long long)grid.x * grid.y * grid.z <= num_sms() && p.total_kblocks / p.splits >= 6 && !getenv("BD_NO_DEEP_RING");
   if (BN == 128) {
-    if (c.b_mn) launch_fprop_t<128, true>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false>(ma0, ma1, mb, mb1, p, grid, st);
+    if (deep) {
+      if (c.b_mn) launch_fprop_t<128, true, 6>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false, 6>(ma0, ma1, mb, mb1, p, grid, st);
+    } else {
+      if (c.b_mn) launch_fprop_t<128, true, 3>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false, 3>(ma0, ma1, mb, mb1, p, grid, st);
+    }
   } else {
-    if (c.b_mn) launch_fprop_t<64, true>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<64, false>(ma0, ma1, mb, mb1, p, grid, st);
+    if (c.b_mn) launch_fprop_t<64, true, 3>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<64, false, 3>(ma0, ma1, mb, mb1, p, grid, st);
   }
   return BD_OK;
 }
@@ -620,10 +628,9 @@ int wgrad_supported(const WgradCall& c) {
   return 1;
 }
 
-template <int BN>
+template <int BN, int kStages>
 static int launch_wgrad_t(const CUtensorMap& a, const CUtensorMap& b, const WgradParams& p, dim3 grid, cudaStream_t st) {
-  constexpr int kStages = 3;  // 3 x 32 KB: two CTAs per SM, so one drains its accumulator while the other streams operands
-  using L = Smem<BN, kStages>;
+  using L = Smem<BN, kStages>;   // 3 stages: two CTAs per SM; 6 stages: one CTA per SM with twice the loads in flight
   auto kern = umma_wgrad_kernel<BN, kStages>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -653,8 +660,11 @@ int wgrad_launch(const WgradCall& c, cudaStream_t st) {
   const int m_tiles = ceil_div(c.Mtot, BM);
   const int tiles = m_tiles * p.n_tiles * c.zcount;
   int splits = 1;
+  const bool deep_ok = getenv("BD_WGRAD_DEEP") != nullptr;   // measured slower (10.25 vs 10.14 ms/step): off by default
   if (c.out_mode == 0) {
-    splits = ceil_div(num_sms(), tiles);
+    // split-K over pixel k-blocks.  With the 6-stage ring: as many splits as keep the grid within one CTA per SM (fewer
+    // partial tiles to reduce atomically); otherwise fill two CTAs per SM
+    splits = deep_ok ? num_sms() / tiles : ceil_div(num_sms(), tiles);
     int maxs = p.kblocks_total / 8 > 0 ? p.kblocks_total / 8 : 1;  // >= 8 k-blocks per CTA
     if (splits > maxs) splits = maxs;
     if (splits < 1) splits = 1;
@@ -684,7 +694,12 @@ int wgrad_launch(const WgradCall& c, cudaStream_t st) {
     if (!make_map(&mb, c.b, 4, dims, str, bbox, es)) return BD_ERR_CUDA;
   }
   dim3 grid(m_tiles * p.n_tiles, c.zcount, splits);
-  if (BN == 128) launch_wgrad_t<128>(ma, mb, p, grid, st); else launch_wgrad_t<64>(ma, mb, p, grid, st);
+  const bool deep = deep_ok && (long long)grid.x * grid.y * grid.z <= num_sms() && p.kblocks_total / splits >= 6;
+  if (BN == 128) {
+    if (deep) launch_wgrad_t<128, 6>(ma, mb, p, grid, st); else launch_wgrad_t<128, 3>(ma, mb, p, grid, st);
+  } else {
+    launch_wgrad_t<64, 3>(ma, mb, p, grid, st);
+  }
   return BD_OK;
 }
 

@@ -753,24 +753,30 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
         const uint32_t rd_addr = stage + (uint32_t)((lane >> 2) * C3P_EPI_PITCH + (lane & 3) * 16);
         const float sc = p.scale;
         __half* ybase = reinterpret_cast<__half*>(p.y) + n_tile * C3_BN + q * 32 + (lane & 3) * 8;
-#pragma unroll 1
-        for (int j0 = phalf * 128; j0 < phalf * 128 + 128; j0 += 16) {
-          uint32_t va[8], vb[8];
-          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + j0;
+        // software pipeline: the TMEM loads of chunk c+1 are in flight while chunk c goes through shared memory
+        uint32_t va[8], vb[8];
+        {
+          const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + phalf * 128;
           tmem_ld_16x256b_x2_nowait(ta, va);
           tmem_ld_16x256b_x2_nowait(ta + (16u << 16), vb);
+        }
+#pragma unroll 1
+        for (int j0 = phalf * 128; j0 < phalf * 128 + 128; j0 += 16) {
           tmem_wait_ld();
+          uint32_t m[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            m[i] = pack_f16x2((__uint_as_float(va[2 * i]) + bq[i & 1]) * sc, (__uint_as_float(va[2 * i + 1]) + bq[i & 1]) * sc);
+            m[4 + i] = pack_f16x2((__uint_as_float(vb[2 * i]) + bq[2 + (i & 1)]) * sc, (__uint_as_float(vb[2 * i + 1]) + bq[2 + (i & 1)]) * sc);
+          }
+          if (j0 + 16 < phalf * 128 + 128) {
+            const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + j0 + 16;
+            tmem_ld_16x256b_x2_nowait(ta, va);
+            tmem_ld_16x256b_x2_nowait(ta + (16u << 16), vb);
+          }
           __syncwarp();   // the previous chunk's read-back is complete
-          stmatrix_x4_trans(st_addr,
-                            pack_f16x2((__uint_as_float(va[0]) + bq[0]) * sc, (__uint_as_float(va[1]) + bq[0]) * sc),
-                            pack_f16x2((__uint_as_float(va[2]) + bq[1]) * sc, (__uint_as_float(va[3]) + bq[1]) * sc),
-                            pack_f16x2((__uint_as_float(va[4]) + bq[0]) * sc, (__uint_as_float(va[5]) + bq[0]) * sc),
-                            pack_f16x2((__uint_as_float(va[6]) + bq[1]) * sc, (__uint_as_float(va[7]) + bq[1]) * sc));
-          stmatrix_x4_trans(st_addr + 32,
-                            pack_f16x2((__uint_as_float(vb[0]) + bq[2]) * sc, (__uint_as_float(vb[1]) + bq[2]) * sc),
-                            pack_f16x2((__uint_as_float(vb[2]) + bq[3]) * sc, (__uint_as_float(vb[3]) + bq[3]) * sc),
-                            pack_f16x2((__uint_as_float(vb[4]) + bq[2]) * sc, (__uint_as_float(vb[5]) + bq[2]) * sc),
-                            pack_f16x2((__uint_as_float(vb[6]) + bq[3]) * sc, (__uint_as_float(vb[7]) + bq[3]) * sc));
+          stmatrix_x4_trans(st_addr, m[0], m[1], m[2], m[3]);
+          stmatrix_x4_trans(st_addr + 32, m[4], m[5], m[6], m[7]);
           __syncwarp();
           // chunk = image rows (j0>>3), (j0>>3)+1 of the block, 8 pixels each; this lane: pixel (lane>>2) of each row
           const int64_t m0 = ((int64_t)n0 * p.H + h0 + (j0 >> 3)) * p.W + w0 + (lane >> 2);

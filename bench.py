@@ -268,6 +268,8 @@ def run_ours(args):
                 "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
                 "traffic": ncu_traffic(), "peak_source": f"{pk['src']} (burst, kernel timed alone)", "ms_per_launch": k_ms,
                 "algorithmic_flops_per_launch": flops,
+                "algorithmic_bytes_per_launch": 2.0 * (2 * B * H * H * C + 9 * C * C),
+                "conv_hbm_gbs_algorithmic": 2.0 * (2 * B * H * H * C + 9 * C * C) / (k_ms / 1e3) / 1e9,
                 "step_tensor_frac_of_sustained": value / world * TRAIN_GFLOP_PER_IMG / 1e3 / pk["tf_sust"]}
         del x, w, y, flush
 
@@ -291,6 +293,38 @@ def run_ours(args):
         except Exception as e:  # sampling is reported, never fatal for the train metric
             samp = {"error": repr(e)}
 
+        # ---- (4b) BASELINE configs[3] shape: DDPM-CELEBA-HQ-256 UNet (113.7 M params), 256x256, per-GPU batch 4
+        celeba = None
+        launches_per_step, loss_scale = int(tr.launches_per_step), tr.loss_scale
+        if world == 1 and not args.no_celeba:
+            try:
+                tr = None
+                torch.cuda.empty_cache()
+                cm = UNet2DModel(**DiffuserModelSched.ARCH["DDPM-CELEBA-HQ-256"]).cuda()
+                cds = SyntheticDataset(256, 3, poison_rate=0.1, seed=7)
+                CB = 4
+                ctr = Trainer(cm, DDPMScheduler(variance_type="fixed_small", clip_sample=True), CB, cds.trigger, cds.target,
+                              lr=8e-5, total_steps=1000, warmup_steps=10)
+                hb = cds.batch(CB, index=0)
+                ctr.load_batch(hb.image, hb.is_poison)
+                for _ in range(3):
+                    ctr.step_resident(True)
+                torch.cuda.synchronize()
+                e0.record()
+                for _ in range(10):
+                    ctr.step_resident(True)
+                e1.record()
+                torch.cuda.synchronize()
+                cms = e0.elapsed_time(e1) / 10
+                celeba = {"workload": "DDPM-CELEBA-HQ-256 poisoned train step, synthetic 3x256x256, per-GPU batch 4",
+                          "ms_per_step": cms, "train_images_per_sec": CB / (cms / 1e3),
+                          "step_tensor_frac_of_sustained": CB / (cms / 1e3) * 1491.1 / 1e3 / pk["tf_sust"],
+                          "loss": float(ctr.loss)}
+                del ctr, cm
+                torch.cuda.empty_cache()
+            except Exception as e:
+                celeba = {"error": repr(e)}
+
         # ---- (5) CPU baseline: the oracle port on this box's host cores, bounded sample
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
@@ -311,10 +345,10 @@ def run_ours(args):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / K},
-            "gpu_launches": int(tr.launches_per_step * K),
-            "launches_per_step": int(tr.launches_per_step),
-            "roofline": roof, "cpu_baseline": cpu, "sampling": samp,
-            "loss": {"resident_last": loss_resident, "e2e_last": last, "loss_scale": tr.loss_scale},
+            "gpu_launches": launches_per_step * K,
+            "launches_per_step": launches_per_step,
+            "roofline": roof, "cpu_baseline": cpu, "sampling": samp, "celebahq_256": celeba,
+            "loss": {"resident_last": loss_resident, "e2e_last": last, "loss_scale": loss_scale},
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -330,6 +364,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=128, help="per-GPU batch")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-celeba", action="store_true", help="skip the CelebA-HQ-256 shaped extra measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -85,6 +85,57 @@ def test_unet_forward_cifar_batch(impl_env, monkeypatch):
     assert mse <= EPS_MSE_TOL
 
 
+def test_celebahq_256_forward_and_train_step():
+    """BASELINE configs[3]: the DDPM-CELEBA-HQ-256 UNet (113.7 M parameters, 6 levels, attention at 16x16 with C = 512)
+    on 256x256 inputs: eps_hat against the CPU oracle (MSE <= 1e-5) and one poisoned training step at the per-GPU batch
+    of the 8-GPU configuration (4): loss against the oracle's, finite gradients, parameters moved by Adam."""
+    from baddiffusion_b200.dataset import Backdoor
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from baddiffusion_b200.train import Trainer
+    from oracle import torch_ref as O
+
+    cfg = O.CELEBAHQ_CONFIG
+    m, sd = _model(cfg, seed=2)
+    S = cfg["sample_size"]
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(1, 3, S, S, generator=g)
+    t = torch.tensor([417])
+    with torch.no_grad():
+        ref = O.unet_forward(sd, cfg, x, t)
+        out = m(x.cuda(), t.cuda()).sample.cpu()
+    mse = float(((out - ref) ** 2).mean())
+    print(f"[celebahq-256 B=1] eps_hat MSE vs oracle: {mse:.3e}; ref std {float(ref.std()):.3f}")
+    assert mse <= EPS_MSE_TOL
+    # one training step, B = 4 (GLASSES -> CAT)
+    B = 4
+    bd = Backdoor(root="datasets")
+    trig = bd.get_trigger(type="GLASSES", channel=3, image_size=S)
+    targ = bd.get_target(type="CAT", trigger=trig)
+    image = torch.randn(B, 3, S, S, generator=g).clamp(-1, 1)
+    isp = torch.tensor([True, False, False, False])
+    tt = torch.randint(0, 1000, (B,), generator=g)
+    noise = torch.randn(B, 3, S, S, generator=g)
+    _, alphas, acp = O.beta_tables()
+    R, x0 = O.poison_blend(image, isp, trig, targ)
+    xn, tgt = O.q_sample(alphas, acp, x0, R, tt, noise)
+    with torch.no_grad():
+        loss_ref = float(((tgt - O.unet_forward(sd, cfg, xn, tt)) ** 2).mean())
+    sched = DDPMScheduler(variance_type="fixed_small")
+    tr = Trainer(m, sched, B, trig, targ, lr=8e-5, total_steps=100, warmup_steps=10, use_graph=False)
+    before = m.flat_params.clone()
+    loss = float(tr.step(image, isp, noise=noise, t=tt))
+    torch.cuda.synchronize()
+    from baddiffusion_b200 import _lib
+    assert _lib.lib().bd_umma_error() == 0
+    print(f"[celebahq-256 B=4] loss {loss:.6f} vs oracle {loss_ref:.6f}; grad norm {tr.grad_norm:.4f}")
+    assert abs(loss - loss_ref) <= 2e-3 * abs(loss_ref)
+    assert math.isfinite(tr.grad_norm) and tr.grad_norm > 0
+    assert float((m.flat_params - before).abs().max()) == 0.0   # cosine warm-up: lr(0) = 0 (optimization.py:134-136)
+    tr.step(image, isp, noise=noise, t=tt)
+    torch.cuda.synchronize()
+    assert float((m.flat_params - before).abs().max()) > 0
+
+
 @pytest.mark.parametrize("name", ["tiny", "cifar10"])
 def test_loss_and_gradients_match_reference(golden, name):
     """p_losses_diffuser fwd/bwd through the autograd bridge vs the reference's autograd gradients."""
