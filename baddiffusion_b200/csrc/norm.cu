@@ -316,6 +316,7 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
 // Against the three-kernel path above this is 1 launch instead of 3 and 4 B/element instead of 6 (forward),
 // 6-8 instead of 10-12 (backward).
 // =============================================================================================================
+constexpr int GN_MAX_CS = 8;    // portable cluster limit; 16 (non-portable) measured 13 % slower per step
 constexpr int GN_VMAX = 4;   // default register-cache depth (vectors per thread); 8 is also compiled (BD_GN_VMAX)
 
 // Block-level reduction of per-thread, per-channel partials (thread (r, v) holds NV values for each of its 8 channels)
@@ -491,8 +492,8 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
 // (gsum): they are the bias gradients of the convolution that made x and, for norm2, the time_emb_proj gradient
 // (D/models/resnet.py:574-580), which otherwise cost one extra pass over dx each.
 // dynamic smem: red[threads][16] f32 | chs[2][C] f32 | chs2[C] f32 | tot[2][C] f32 | gab[G][2] f32
-template <int VMAX>
-__global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
+template <int VMAX, int MINB>
+__global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
     const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
@@ -581,9 +582,9 @@ __global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
   }
   cl.sync();
   for (int ch = tid; ch < C; ch += blockDim.x) {
-    float ra[8], rx[8];   // remote loads first, adds after (one DSMEM round trip)
+    float ra[GN_MAX_CS], rx[GN_MAX_CS];   // remote loads first, adds after (one DSMEM round trip)
 #pragma unroll
-    for (int rk = 0; rk < 8; ++rk)
+    for (int rk = 0; rk < GN_MAX_CS; ++rk)
       if (rk < CS) {
         const float* rc = cl.map_shared_rank(chs, rk);
         ra[rk] = rc[ch];
@@ -591,7 +592,7 @@ __global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
       }
     float sa = 0.f, sx = 0.f;
 #pragma unroll
-    for (int rk = 0; rk < 8; ++rk)
+    for (int rk = 0; rk < GN_MAX_CS; ++rk)
       if (rk < CS) { sa += ra[rk]; sx += rx[rk]; }
     // sum dz*xhat = rstd * (sum dz*x - mean * sum dz)
     const int g = ch / cpg;
@@ -688,13 +689,13 @@ __global__ void __launch_bounds__(256, VMAX == 0 ? 3 : 2) gn_bwd_fused_kernel(
     gn_block_channel_sums<1>(red, chs2, so, rows, C8, C, r, v);  // red[] was last read before the cluster barrier above
     cl.sync();
     for (int ch = rank * blockDim.x + tid; ch < C; ch += CS * blockDim.x) {
-      float ra[8];
+      float ra[GN_MAX_CS];
 #pragma unroll
-      for (int rk = 0; rk < 8; ++rk)
+      for (int rk = 0; rk < GN_MAX_CS; ++rk)
         if (rk < CS) ra[rk] = cl.map_shared_rank(chs2, rk)[ch];
       float sa = 0.f;
 #pragma unroll
-      for (int rk = 0; rk < 8; ++rk)
+      for (int rk = 0; rk < GN_MAX_CS; ++rk)
         if (rk < CS) sa += ra[rk];
       gsum[(int64_t)b * ld_gsum + ch] = sa;
     }
@@ -716,6 +717,7 @@ static int gn_env_int(const char* name, int dflt) {
 }
 
 static bool gn_fused_geometry(int B, int HW, int C, int max_threads, int vmax, int* threads, int* cs) {
+  const int max_cs = GN_MAX_CS;
   if (getenv("BD_GN_V1")) return false;
   const int C8 = C / 8;
   if (C8 > max_threads || C8 < 1) return false;
@@ -724,7 +726,7 @@ static bool gn_fused_geometry(int B, int HW, int C, int max_threads, int vmax, i
   if (rows < 1) rows = 1;
   *threads = C8 * rows;
   int c = 1;
-  while (c < 8 && ceil_div(ceil_div(HW, c), rows) > vmax) c *= 2;
+  while (c < max_cs && ceil_div(ceil_div(HW, c), rows) > vmax) c *= 2;
   while (c < 8 && (int64_t)B * c < num_sms() && HW / (2 * c) >= rows) c *= 2;
   if (ceil_div(ceil_div(HW, c), rows) > 32) return false;
   *cs = c;
@@ -822,7 +824,9 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
     if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs)) {
       const size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
       const bool stream_bwd = gn_env_int("BD_GN_BWD_STREAM", 0) != 0;
-      cudaError_t e = launch_cluster(stream_bwd ? gn_bwd_fused_kernel<0> : vmax == 4 ? gn_bwd_fused_kernel<4> : gn_bwd_fused_kernel<8>, dim3(cs, B), fthreads, smem,
+      // register budget: 128 / thread (2 blocks of 256); 80 or 64 registers spill 400-570 B per thread
+      cudaError_t e = launch_cluster(stream_bwd ? gn_bwd_fused_kernel<0, 3> : vmax == 8 ? gn_bwd_fused_kernel<8, 2> : gn_bwd_fused_kernel<4, 2>,
+                                     dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
                                      (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
                                      dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu);
