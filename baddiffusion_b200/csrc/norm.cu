@@ -12,7 +12,12 @@ namespace cg = cooperative_groups;
 
 namespace bd {
 
-constexpr int kGnMaxSplits = 32;
+// upper bound of the per-sample split count of the three-kernel path: 32 at training batch sizes, more when few large
+// samples (CelebA-HQ: 4 samples of 256 x 256 per GPU) would otherwise leave most SMs without a block
+static inline int gn_max_splits(int B) {
+  int s = ceil_div(4 * num_sms(), B > 0 ? B : 1);
+  return s < 32 ? 32 : (s > 256 ? 256 : s);
+}
 constexpr int UNR = 4;
 
 // SiLU and its derivative from ONE special-function op.  These kernels are bound by the 16-lane MUFU pipe, not by HBM:
@@ -40,7 +45,7 @@ static inline int gn_splits(int B, int HW, int rows, int per_sm) {
   if (want < 1) want = 1;
   int cap = HW / (rows * UNR) > 0 ? HW / (rows * UNR) : 1;
   int s = want < cap ? want : cap;
-  if (s > kGnMaxSplits) s = kGnMaxSplits;
+  if (s > gn_max_splits(B)) s = gn_max_splits(B);
   return s < 1 ? 1 : s;
 }
 
@@ -758,7 +763,7 @@ extern "C" {
 
 size_t bd_gn_workspace_floats(int B, int C) {
   // forward needs B*splits*G*2 (G <= C), backward B*splits*2*C
-  return (size_t)(B > 0 ? B : 1) * (kGnMaxSplits * 2 * (size_t)C + 2 * (size_t)C);
+  return (size_t)(B > 0 ? B : 1) * ((size_t)gn_max_splits(B) * 2 * (size_t)C + 2 * (size_t)C);
 }
 
 static inline void gn_geometry(int B, int HW, int C, int per_sm, int* threads, int* rows, int* splits, int* asplits) {

@@ -13,11 +13,13 @@ from baddiffusion_b200.unet import UNet2DModel
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 what = sys.argv[2] if len(sys.argv) > 2 else "train"
+arch = sys.argv[3] if len(sys.argv) > 3 else "DDPM-CIFAR10-32"
+S = 256 if "256" in arch else 32
 _lib.lib()
 torch.manual_seed(0)
-model = UNet2DModel(**DiffuserModelSched.ARCH["DDPM-CIFAR10-32"]).cuda()
+model = UNet2DModel(**DiffuserModelSched.ARCH[arch]).cuda()
 sched = DDPMScheduler(variance_type="fixed_large")
-ds = SyntheticDataset(32, 3, poison_rate=0.1)
+ds = SyntheticDataset(S, 3, poison_rate=0.1)
 tr = Trainer(model, sched, B, ds.trigger, ds.target, use_graph=False)
 hb = ds.batch(B)
 tr.load_batch(hb.image, hb.is_poison)
