@@ -243,7 +243,10 @@ class UNetEngine:
         # ---- down path
         k = 1
         H = S
+        self._n_emitters_before_down1 = None
         for i, b in enumerate(topo["down"]):
+            if i == 1:
+                self._n_emitters_before_down1 = len(self._bwd_emitters)
             for j in range(len(b["resnets"])):
                 dest = skip_acts[k]
                 if b["attn"]:
@@ -271,6 +274,7 @@ class UNetEngine:
             h = m2
         self._resnet("mid_block.resnets.1.", h, x_slots[0], scale=ms)
         # ---- up path
+        self._n_emitters_before_up = len(self._bwd_emitters)
         n = 0
         for i, b in enumerate(topo["up"]):
             nres = len(b["resnets"])
@@ -299,6 +303,34 @@ class UNetEngine:
         if self.train:
             for emit in reversed(self._bwd_emitters):
                 emit()
+            # Backward in three parts for the data-parallel trainer: every emitter appended exactly one op, so part
+            # boundaries are emitter counts.  After part i the GEMM weight gradients of the layers it covered are final
+            # (`bwd_parts[i][2]`, contiguous ranges of the flat buffer) and can be all-reduced while the next part runs:
+            #   0: conv_out + up path        1: mid block + down blocks 1..      2: down block 0, conv_in, timestep path
+            assert len(self.bwd) == len(self._bwd_emitters)
+            ne = len(self._bwd_emitters)
+            k0 = ne - self._n_emitters_before_up
+            k1 = ne - (self._n_emitters_before_down1 if self._n_emitters_before_down1 is not None else 0)
+
+            def ranges_of(pred):
+                segs = sorted((self.lay.offset[k], self.lay.offset[k] + math.prod(self.lay.entries[k])) for k in self.lay.offset
+                              if pred(k) and self.lay.offset[k] < self.lay.tproj_w_offset and self.lay.offset[k] + math.prod(self.lay.entries[k]) <= self.lay.tproj_w_offset)
+                out = []
+                for lo, hi in segs:
+                    if out and lo - out[-1][1] < self.lay.ALIGN:   # alignment padding only
+                        out[-1][1] = hi
+                    else:
+                        out.append([lo, hi])
+                for lo, hi in out:   # nothing else lives inside a range
+                    for k, o in self.lay.offset.items():
+                        assert pred(k) or not (lo <= o < hi), (k, lo, hi)
+                return [tuple(r) for r in out]
+
+            nd = len(self.topo["down"])
+            late = tuple(f"down_blocks.{i}." for i in range(1, nd)) + ("mid_block.",)
+            self.bwd_parts = [(0, k0, ranges_of(lambda k: k.startswith("up_blocks."))),
+                              (k0, k1, ranges_of(lambda k: k.startswith(late))),
+                              (k1, None, [])]
             if self._bias_jobs:
                 rows = [[gs.data_ptr(), gs.stride(0), g.data_ptr(), g.numel()] for gs, g in self._bias_jobs]
                 self._bias_table = torch.tensor(rows, dtype=torch.int64, device=dev)
@@ -621,8 +653,14 @@ class UNetEngine:
         for f in self.fwd:
             f()
 
-    def run_backward(self):
-        for f in self.bwd:
+    def run_backward(self, part: Optional[int] = None):
+        """part None: everything; i: the ops of `bwd_parts[i]`.  Each part ends with the side stream joined."""
+        if part is None:
+            ops_ = self.bwd
+        else:
+            a, b, _ = self.bwd_parts[part]
+            ops_ = self.bwd[a:b]   # b None: through the batched bias / dgamma / dbeta launch appended after the emitters
+        for f in ops_:
             f()
         self._join()
 

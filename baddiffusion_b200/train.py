@@ -82,12 +82,21 @@ class Trainer:
         self.seed = seed
         self.host_step = 0
         self._g_fb = None
+        self._g_fb2 = None
         self._g_opt = None
+        # data parallel: all-reduce the up-path gradients (the larger, contiguous half of the buffer) while the rest of
+        # backward runs, the remainder at the end (BD_NO_AR_OVERLAP=1: one all-reduce after backward)
+        self.overlap_allreduce = self.world > 1 and os.environ.get("BD_NO_AR_OVERLAP", "0") != "1"
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------ the kernel sequence
-    def _fwd_bwd(self, philox_noise: bool):
+    def _fwd_bwd(self, philox_noise: bool, part: Optional[int] = None):
+        """part None: the whole sequence; 0: everything up to the end of the first backward part; i > 0: backward part i
+        (the data-parallel step all-reduces the finished gradient ranges in between, see UNetEngine.bwd_parts)."""
         eng = self.eng
+        if part is not None and part > 0:
+            eng.run_backward(part)
+            return
         ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16)
         ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
                        noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
@@ -97,7 +106,7 @@ class Trainer:
         eng.run_forward()
         ops.mse_fwd_bwd(eng.eps_hat, self.eps_target, self.loss, self.d_eps, self.mse_part, self.state[0:1])
         self.gflat.zero_()
-        eng.run_backward()
+        eng.run_backward(part)
 
     def _optimizer(self):
         ops.grad_norm(self.gflat, self.norm_part, self.state)
@@ -124,7 +133,11 @@ class Trainer:
         snap = (self.flat.clone(), self.m.clone(), self.v.clone(), self.state.clone(), self.step_dev.clone(),
                 self.iter_dev.clone())
         before = ops.launch_count()
-        self._g_fb = self._capture(lambda: self._fwd_bwd(philox_noise))
+        if self.overlap_allreduce:
+            self._g_fb = self._capture(lambda: self._fwd_bwd(philox_noise, 0))
+            self._g_fb2 = [self._capture(lambda i=i: self._fwd_bwd(philox_noise, i)) for i in range(1, len(self.eng.bwd_parts))]
+        else:
+            self._g_fb = self._capture(lambda: self._fwd_bwd(philox_noise))
         self._g_opt = self._capture(self._optimizer)
         self.launches_per_step = (ops.launch_count() - before) // 2 + 1  # + the memset of the gradient buffer
         for dst, src in zip((self.flat, self.m, self.v, self.state, self.step_dev, self.iter_dev), snap):
@@ -156,11 +169,33 @@ class Trainer:
         if self.use_graph:
             self._ensure_graphs(philox_noise)
             assert self._philox == philox_noise, "noise mode is baked into the captured graph"
-            self._g_fb.replay()
+        dist = torch.distributed
+        if self.overlap_allreduce:
+            # backward part i+1 runs while NCCL (its own stream) averages the gradient ranges part i finished
+            parts = self.eng.bwd_parts
+            works, covered = [], []
+            for i in range(len(parts)):
+                if self.use_graph:
+                    (self._g_fb if i == 0 else self._g_fb2[i - 1]).replay()
+                else:
+                    self._fwd_bwd(philox_noise, i)
+                for lo, hi in parts[i][2]:
+                    works.append(dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+                    covered.append((lo, hi))
+            pos = 0
+            for lo, hi in sorted(covered) + [(self.gflat.numel(), self.gflat.numel())]:   # whatever no part claimed
+                if lo > pos:
+                    works.append(dist.all_reduce(self.gflat[pos:lo], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
+                pos = max(pos, hi)
+            for w in works:
+                w.wait()
         else:
-            self._fwd_bwd(philox_noise)
-        if self.world > 1:
-            torch.distributed.all_reduce(self.gflat, op=torch.distributed.ReduceOp.AVG, group=self.pg)
+            if self.use_graph:
+                self._g_fb.replay()
+            else:
+                self._fwd_bwd(philox_noise)
+            if self.world > 1:
+                dist.all_reduce(self.gflat, op=dist.ReduceOp.AVG, group=self.pg)
         if self.use_graph:
             self._g_opt.replay()
         else:
