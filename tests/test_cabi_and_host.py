@@ -153,3 +153,41 @@ def test_scheduler_config_roundtrip(tmp_path):
     assert len([k for k in j if not k.startswith("_")]) == 14  # Appendix D: 14 DDPMScheduler args
     s2 = DDPMScheduler.from_pretrained(str(tmp_path))
     assert dict(s2.config) == dict(s.config)
+
+
+@pytest.mark.parametrize("arch", ["DDPM-CIFAR10-32", "DDPM-CELEBA-HQ-256"])
+def test_flat_layout_gradient_buckets_are_contiguous(arch):
+    """The data-parallel trainer all-reduces the gradient buffer in address ranges that become final part-way through
+    backward (up blocks first, then mid + down blocks 1.., then the rest): FlatLayout must keep the tensor-core weights
+    of each of those layer groups contiguous, with no other parameter inside the range."""
+    import math
+
+    from baddiffusion_b200.model import DiffuserModelSched
+    from baddiffusion_b200.unet import FlatLayout
+    from baddiffusion_b200.unet import UNet2DModel
+
+    lay = UNet2DModel(**DiffuserModelSched.ARCH[arch]).layout
+    assert isinstance(lay, FlatLayout)
+
+    def ranges(pred):
+        segs = sorted((lay.offset[k], lay.offset[k] + math.prod(lay.entries[k])) for k in lay.offset
+                      if pred(k) and lay.offset[k] + math.prod(lay.entries[k]) <= lay.tproj_w_offset)
+        out = []
+        for lo, hi in segs:
+            if out and lo - out[-1][1] < lay.ALIGN:
+                out[-1][1] = hi
+            else:
+                out.append([lo, hi])
+        return out
+
+    up = ranges(lambda k: k.startswith("up_blocks."))
+    assert len(up) == 1
+    nd = sum(1 for k in lay.offset if k.endswith("resnets.0.conv1.weight") and k.startswith("down_blocks."))
+    late = tuple(f"down_blocks.{i}." for i in range(1, nd)) + ("mid_block.",)
+    lt = ranges(lambda k: k.startswith(late))
+    assert 1 <= len(lt) <= 2
+    for (lo, hi), pref in [(up[0], ("up_blocks.",))] + [(r, late) for r in lt]:
+        for k, o in lay.offset.items():
+            assert k.startswith(pref) or not (lo <= o < hi), (k, lo, hi)
+    covered = sum(hi - lo for lo, hi in up + lt)
+    assert covered > 0.8 * lay.n_gemm   # the overlapped buckets carry most of the gradient bytes
