@@ -836,7 +836,9 @@ int bd_conv_out_fwd(const void* x, int64_t ld_x, const float* w_packed, const fl
 
 int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const float* dy_nchw, void* dx, int64_t ld_dx,
                     float* dw, float* dbias, int B, int Cin, int H, int W, int Cout, int accumulate, void* stream) {
-  BD_CHECK_ARG(x && w_packed && dy_nchw && dx && dw && Cout > 0 && Cout <= 4 && Cin % 8 == 0 && ld_dx % 8 == 0, "bd_conv_out_bwd: bad argument");
+  // dx == nullptr: parameter gradients only; dw == nullptr: data gradient only (the engine runs the two halves on
+  // different streams: only the data gradient is on the critical path of backward)
+  BD_CHECK_ARG(x && w_packed && dy_nchw && (dx || dw) && Cout > 0 && Cout <= 4 && Cin % 8 == 0 && ld_dx % 8 == 0, "bd_conv_out_bwd: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   size_t smem = (size_t)Cout * Cin * 9 * sizeof(float);
   BD_CHECK_ARG(smem <= 200 * 1024, "bd_conv_out_bwd: Cin too large");
@@ -845,9 +847,13 @@ int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const fl
   int grid = (int)((total + 255) / 256);
   if (grid > 4 * num_sms()) grid = 4 * num_sms();
   const bool fast = getenv("BD_NO_CONVIO") == nullptr;
-  if (!(fast && conv_out_dgrad_fast(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout, st))) {
+  if (dx && !(fast && conv_out_dgrad_fast(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout, st))) {
     conv_out_dgrad_kernel<<<grid, 256, smem, st>>>(w_packed, dy_nchw, (__half*)dx, ld_dx, B, Cin, H, W, Cout);
     count_launch(1);
+  }
+  if (!dw) {
+    BD_CHECK_LAUNCH();
+    return BD_OK;
   }
   if (!accumulate) {
     zero_f32_kernel<<<ceil_div((size_t)Cout * Cin * 9, 2048), 256, 0, st>>>(dw, (size_t)Cout * Cin * 9);

@@ -237,7 +237,8 @@ class UNetEngine:
         if self.train:
             gw_in, gb_in = self.G32("conv_in.weight"), self.G32("conv_in.bias")
             self._bwd_emitters.append(lambda: self.bwd.append(
-                lambda: ops.conv_in_wgrad(self.io["x"], h0.g, gw_in, gb_in, accumulate=True)))
+                # a parameter gradient: side stream, next to the timestep-path tail instead of in front of it
+                lambda: self._fork(lambda: ops.conv_in_wgrad(self.io["x"], h0.g, gw_in, gb_in, accumulate=True))))
         h = h0
 
         # ---- down path
@@ -588,7 +589,8 @@ class UNetEngine:
             assert not x.g_filled
 
             def bw():
-                ops.conv_out_bwd(a, w, self.io["d_eps"], d_a, g_w, g_b, accumulate=True)
+                self._fork(lambda: ops.conv_out_bwd(a, w, self.io["d_eps"], None, g_w, g_b, accumulate=True))  # parameter gradients
+                ops.conv_out_bwd(a, w, self.io["d_eps"], d_a, None, None, accumulate=True)                        # data gradient
                 self._gn_bwd(x.t, d_a, x.g, nw, nb, st, g_nw, g_nb, True, gsum=x.gs)
 
             self.bwd.append(bw)

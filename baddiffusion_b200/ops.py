@@ -216,7 +216,7 @@ def conv_out_fwd(x, w_packed, bias, y_nchw):
 
 def conv_out_bwd(x, w_packed, dy_nchw, dx, dw, dbias, accumulate=False):
     px, ldx, B, H, W, Cin = _view(x)
-    check(L.lib().bd_conv_out_bwd(px, ldx, _p(w_packed), _p(dy_nchw), dx.data_ptr(), dx.stride(2), _p(dw), _p(dbias),
+    check(L.lib().bd_conv_out_bwd(px, ldx, _p(w_packed), _p(dy_nchw), _p(dx), dx.stride(2) if dx is not None else 8, _p(dw), _p(dbias),
                                   B, Cin, H, W, dy_nchw.shape[1], int(accumulate), _s()))
 
 

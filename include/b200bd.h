@@ -188,7 +188,8 @@ int bd_conv_in_fwd(const float* x_nchw, const float* w_packed, const float* bias
                    int H, int W, int Cout, void* stream);
 int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* dw, float* dbias, int B, int Cin,
                      int H, int W, int Cout, int accumulate, void* stream);
-/* conv_out (f16 NHWC in -> Cout=3 f32 NCHW eps_hat), unet_2d.py:217,314; and its backward */
+/* conv_out (f16 NHWC in -> Cout=3 f32 NCHW eps_hat), unet_2d.py:217,314; and its backward.  bd_conv_out_bwd: dx nullable
+ * (parameter gradients only) or dw nullable (data gradient only): the two halves may run on different streams.          */
 int bd_conv_out_fwd(const void* x, int64_t ld_x, const float* w_packed, const float* bias, float* y_nchw, int B, int Cin,
                     int H, int W, int Cout, void* stream);
 int bd_conv_out_bwd(const void* x, int64_t ld_x, const float* w_packed, const float* dy_nchw, void* dx, int64_t ld_dx,
