@@ -190,6 +190,7 @@ class UNetEngine:
 
         def f_temb():
             ops.temb_mlp(self.io["t"], w1, b1, w2, b2, self.emb, self.semb16, self.freqs, self.sin, self.h1, flip=flip)
+            self._join()   # the trainer refreshes the fp16 weight shadow on the side stream while the fp32 MLP above runs
             ops.conv_fwd(self.semb16.view(1, 1, B, temb_dim), wtp16, self.tproj.view(1, 1, B, ncol), ksize=1, bias=btp,
                          impl=self.impl)
 

@@ -97,7 +97,10 @@ class Trainer:
         if part is not None and part > 0:
             eng.run_backward(part)
             return
-        ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16)
+        # fp16 shadow of the GEMM weights and the gradient memset run on the side stream under batch-prep and the timestep
+        # MLP; the engine joins before its first tensor-core GEMM (f_temb) and this function before backward
+        eng._fork(lambda: ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16))
+        eng._fork(self.gflat.zero_)
         ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
                        noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
                        x_noisy=self.x_noisy, eps_target=self.eps_target, noise_out=None, noise_counter=self.iter_dev)
@@ -105,7 +108,7 @@ class Trainer:
         eng.io["x"], eng.io["t"], eng.io["d_eps"] = self.x_noisy, self.t, self.d_eps
         eng.run_forward()
         ops.mse_fwd_bwd(eng.eps_hat, self.eps_target, self.loss, self.d_eps, self.mse_part, self.state[0:1])
-        self.gflat.zero_()
+        eng._join()                   # gradient writers on the main stream (timestep path) are ordered after the memset
         eng.run_backward(part)
 
     def _optimizer(self):
