@@ -224,6 +224,174 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
 }
 
 // =============================================================================================
+// Persistent fprop kernel for grids with many small-K tiles (1x1 convs / Linears / attention GEMMs at 16x16 and up:
+// K = 256-768 is 4-12 k-blocks, so a one-tile CTA spends most of its ~10 us life in fixed costs -- barrier init, TMEM
+// allocation, first TMA round trip, epilogue drain, teardown).  One CTA per SM walks tiles t = blockIdx.x, += gridDim.x:
+//   * the producer streams the operands of consecutive tiles through one ring without a break;
+//   * TWO TMEM accumulators (2 x BN columns): the MMA warp fills buffer t&1 while the epilogue warps drain the other,
+//     handed over with tmem_full[2] / tmem_empty[2] barriers;
+//   * the epilogue's fp32 staging tiles have their own shared memory (in the one-tile kernel they alias the operand
+//     ring, which must be idle for that).
+// Same operands, segment list and epilogue (`epilogue_warp`) as umma_fprop_kernel: results are bit-identical.
+// =============================================================================================
+template <int BN, int kStages>
+struct SmemP {
+  static constexpr int kABytes = BM * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kEpiOffset = kStages * kStageBytes;
+  static constexpr int kEpiBytes = 8 * 32 * (BN / 2 + 4) * 4;
+  static constexpr int kBarOffset = kEpiOffset + kEpiBytes;
+  static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
+};
+
+template <int BN, int kStages, bool B_MN>
+__global__ void __launch_bounds__(320, 1) umma_fprop_persistent_kernel(const __grid_constant__ CUtensorMap tmA0,
+                                                                       const __grid_constant__ CUtensorMap tmA1,
+                                                                       const __grid_constant__ CUtensorMap tmB0,
+                                                                       const __grid_constant__ CUtensorMap tmB1,
+                                                                       const FpropParams p, const int m_tiles,
+                                                                       const int n_tiles) {
+  using L = SmemP<BN, kStages>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
+  uint64_t* empty = full + kStages;
+  uint64_t* tmem_full = empty + kStages;    // [2]
+  uint64_t* tmem_empty = tmem_full + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = m_tiles * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA0);
+    prefetch_tmap(&tmA1);
+    prefetch_tmap(&tmB0);
+    prefetch_tmap(&tmB1);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 8);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    // ===== TMA producer: free-running over all tiles of this CTA =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x) {
+        const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;   // n fastest: neighbours share the A tile in L2
+        const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.bw, h0 = th * p.bh, n0 = tn * p.bn;
+        for (int s = 0; s < p.nseg && ok; ++s) {
+          const KSeg sg = p.seg[s];
+          const CUtensorMap* mapA = sg.a_src ? &tmA1 : &tmA0;
+          const CUtensorMap* mapB = sg.b_src ? &tmB1 : &tmB0;
+          for (int kb = 0; kb < sg.nblk; ++kb) {
+            ok = mbar_wait(&empty[stage], phase ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            uint8_t* sa = smem + stage * L::kStageBytes;
+            uint8_t* sb = sa + L::kABytes;
+            mbar_expect_tx(&full[stage], L::kStageBytes);
+            tma_load_4d(mapA, &full[stage], sa, sg.a_c0 + kb * BK, w0 * p.a_stride + sg.dx, h0 * p.a_stride + sg.dy, n0);
+            const int bz = sg.b_z + (p.batched ? n0 : 0);
+            if (!B_MN) {
+              tma_load_3d(mapB, &full[stage], sb, sg.b_k0 + kb * BK, n_tile * BN, bz);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_3d(mapB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, sg.b_k0 + kb * BK, bz);
+            }
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0, eph[2] = {0, 0};
+      bool ok = true;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
+        const int buf = lt & 1;
+        ok = mbar_wait(&tmem_empty[buf], eph[buf] ^ 1, p.error_flag, 4);   // drained by the epilogue two tiles ago
+        if (!ok) break;
+        eph[buf] ^= 1;
+        tc_fence_after();
+        for (int it = 0; it < p.total_kblocks; ++it) {
+          ok = mbar_wait(&full[stage], phase, p.error_flag, 2);
+          if (!ok) break;
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+          const uint32_t sb = sa + L::kABytes;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t ad = make_desc(sa + k * 32, p.a_lbo, p.a_sbo);
+            const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
+            umma_f16(tmem_base + buf * BN, ad, bd, p.idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(&tmem_full[buf]);
+      }
+    }
+  } else {
+    // ===== epilogue: 8 warps, warp w owns TMEM lanes 32*(w%4) .. +31 and column half (w-2)/4 =====
+    const int q = warp & 3;
+    const int half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const int dn = r / (p.bw * p.bh), dh = (r / p.bw) % p.bh, dw = r % p.bw;
+    float* stage = reinterpret_cast<float*>(smem + L::kEpiOffset) + (warp - 2) * 32 * (BN / 2 + 4);
+    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+    uint32_t fph[2] = {0, 0};
+    bool ok = true;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total && ok; tile += gridDim.x, ++lt) {
+      const int buf = lt & 1;
+      const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+      const int tw = m_tile % p.tiles_w, th = (m_tile / p.tiles_w) % p.tiles_h, tn = m_tile / (p.tiles_w * p.tiles_h);
+      const int n = tn * p.bn + dn, h = th * p.bh + dh, w = tw * p.bw + dw;
+      const bool valid = n < p.NB && h < p.H && w < p.W;
+      const int64_t mlin = ((int64_t)n * p.H + h) * p.W + w;
+      const int64_t m = (int64_t)n * p.out_sn + h * p.out_sh + w * p.out_sw + p.out_off;
+      ok = mbar_wait(&tmem_full[buf], fph[buf], p.error_flag, 3);
+      if (!ok) break;
+      fph[buf] ^= 1;
+      tc_fence_after();
+      epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2), stage, lane, m, mlin, valid,
+                            n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 2 * BN);
+  }
+}
+
+// =============================================================================================
 // wgrad-style kernel: both operands MN-major, K = pixels.  grid (m_tiles*n_tiles, z, splits)
 // =============================================================================================
 template <int BN, int kStages>
@@ -594,6 +762,24 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
     while (p.splits < 4 && tiles * p.splits * 2 <= budget && p.total_kblocks / (p.splits * 2) >= 6) p.splits *= 2;
   }
   dim3 grid(m_tiles, c.N / BN, p.splits);
+  // many small-K tiles: persistent kernel (one CTA per SM, double-buffered TMEM)
+  if (BN == 128 && p.splits == 1 && (long long)m_tiles * (c.N / BN) > 2 * num_sms() && p.total_kblocks <= 16 && p.dbg_shift == 0 &&
+      !getenv("BD_NO_FPROP_PERSIST")) {
+    constexpr int kSt = 4;
+    using LP = SmemP<128, kSt>;
+    const int nt = c.N / BN;
+    const int ctas = num_sms();
+    static bool pattr[2] = {false, false};
+    if (c.b_mn) {
+      if (!pattr[1]) { cudaFuncSetAttribute(umma_fprop_persistent_kernel<128, kSt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal); pattr[1] = true; }
+      launch_pdl(umma_fprop_persistent_kernel<128, kSt, true>, dim3(ctas), dim3(320), (size_t)LP::kTotal, st, ma0, ma1, mb, mb1, p, m_tiles, nt);
+    } else {
+      if (!pattr[0]) { cudaFuncSetAttribute(umma_fprop_persistent_kernel<128, kSt, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal); pattr[0] = true; }
+      launch_pdl(umma_fprop_persistent_kernel<128, kSt, false>, dim3(ctas), dim3(320), (size_t)LP::kTotal, st, ma0, ma1, mb, mb1, p, m_tiles, nt);
+    }
+    count_launch(1);
+    return BD_OK;
+  }
   const bool deep = (long long)grid.x * grid.y * grid.z <= num_sms() && p.total_kblocks / p.splits >= 6 && !getenv("BD_NO_DEEP_RING");
   if (BN == 128) {
     if (deep) {

@@ -367,6 +367,35 @@ def test_conv3_bench_sized_kernels(ops, B, H, Cin, Cout):
     assert (to_nchw(dx) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
 
 
+@pytest.mark.parametrize("B,H,Cin,Cout", [(128, 16, 256, 256), (128, 16, 256, 768), (40, 32, 384, 128), (130, 16, 512, 256)])
+def test_conv1x1_persistent_kernel(ops, monkeypatch, B, H, Cin, Cout):
+    """1x1 convs / Linears with many small-K tiles run on the persistent generic kernel (one CTA per SM, two TMEM
+    accumulators): forward with every epilogue term and dgrad against torch, and bitwise against the one-tile-per-CTA
+    kernel (same accumulation order, same epilogue)."""
+    im = ops.L.BD_IMPL_UMMA
+    x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, 1, seed=5)
+    bias = torch.randn(Cout, device="cuda")
+    rowbias = torch.randn(B, Cout, device="cuda")
+    res, resr = nhwc_half(torch.randn(B, Cout, H, H, device="cuda"))
+    y = torch.empty(B, H, H, Cout, dtype=torch.half, device="cuda")
+    ops.conv_fwd(x, w, y, ksize=1, bias=bias, rowbias=rowbias, residual=res, scale=0.5, impl=im)
+    assert ops.umma_error() == 0
+    ref = (F.conv2d(xr, wr, bias) + rowbias[:, :, None, None] + resr) * 0.5
+    assert (to_nchw(y) - ref).abs().max() < 3e-3 * max(1.0, float(ref.abs().max()))
+    dy, dyr = nhwc_half(torch.randn(B, Cout, H, H, device="cuda"))
+    add, addr = nhwc_half(torch.randn(B, Cin, H, H, device="cuda"))
+    dx = torch.empty(B, H, H, Cin, dtype=torch.half, device="cuda")
+    ops.conv_dgrad(dy, w, dx, ksize=1, residual=add, impl=im)
+    assert ops.umma_error() == 0
+    refd = torch.nn.grad.conv2d_input(xr.shape, wr, dyr) + addr
+    assert (to_nchw(dx) - refd).abs().max() < 3e-3 * max(1.0, float(refd.abs().max()))
+    monkeypatch.setenv("BD_NO_FPROP_PERSIST", "1")
+    y2, dx2 = torch.empty_like(y), torch.empty_like(dx)
+    ops.conv_fwd(x, w, y2, ksize=1, bias=bias, rowbias=rowbias, residual=res, scale=0.5, impl=im)
+    ops.conv_dgrad(dy, w, dx2, ksize=1, residual=add, impl=im)
+    assert torch.equal(y, y2) and torch.equal(dx, dx2)
+
+
 @pytest.mark.parametrize("impl", ["simt", "umma"])
 @pytest.mark.parametrize("pad,B,H,Cc", [(0, 3, 16, 128), (1, 3, 16, 128), (0, 2, 32, 128), (0, 5, 8, 256)])
 def test_conv_stride2(ops, impl, pad, B, H, Cc):
