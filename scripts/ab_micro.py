@@ -54,8 +54,8 @@ if what in ("all", "gn"):
             out.append((tf, tb))
         setenv("BD_GN_V1", False)
         print(f"GN B={B} H={H} C={C} ({mb:.1f} MB): fwd v1 {out[0][0]:.1f} us -> fused {out[1][0]:.1f} us "
-              f"({2 * mb / out[1][0] / 1e3:.2f} TB/s alg);  bwd(+add,+gsum) v1 {out[0][1]:.1f} us -> fused {out[1][1]:.1f} us "
-              f"({4 * mb / out[1][1] / 1e3:.2f} TB/s alg)", flush=True)
+              f"({2 * mb / out[1][0]:.2f} TB/s alg);  bwd(+add,+gsum) v1 {out[0][1]:.1f} us -> fused {out[1][1]:.1f} us "
+              f"({4 * mb / out[1][1]:.2f} TB/s alg)", flush=True)
 
 if what in ("all", "conv"):
     for (B, H, Cin, Cout, res) in [(128, 32, 128, 128, False), (128, 32, 128, 128, True), (128, 32, 256, 128, True), (128, 32, 256, 256, False),
