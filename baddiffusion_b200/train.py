@@ -31,6 +31,16 @@ def cosine_lr_lambda(step: int, warmup: int, total: int, num_cycles: float = 0.5
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
 
 
+def uncovered_ranges(covered, n):
+    """[lo, hi) ranges of [0, n) that no range of `covered` touches (the gradient bytes left for the last all-reduce)."""
+    out, pos = [], 0
+    for lo, hi in sorted(covered) + [(n, n)]:
+        if lo > pos:
+            out.append((pos, lo))
+        pos = max(pos, hi)
+    return out
+
+
 class Trainer:
     def __init__(self, model: UNet2DModel, noise_sched: DDPMScheduler, batch: int, trigger: torch.Tensor,
                  target: torch.Tensor, lr: float = 2e-4, total_steps: int = 23450, warmup_steps: int = 500,
@@ -185,11 +195,8 @@ class Trainer:
                 for lo, hi in parts[i][2]:
                     works.append(dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
                     covered.append((lo, hi))
-            pos = 0
-            for lo, hi in sorted(covered) + [(self.gflat.numel(), self.gflat.numel())]:   # whatever no part claimed
-                if lo > pos:
-                    works.append(dist.all_reduce(self.gflat[pos:lo], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
-                pos = max(pos, hi)
+            for lo, hi in uncovered_ranges(covered, self.gflat.numel()):   # whatever no part claimed
+                works.append(dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
             for w in works:
                 w.wait()
         else:

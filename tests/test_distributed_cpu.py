@@ -95,3 +95,16 @@ def test_shard_for_rank_properties():
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(s for s in sizes if s >= 0) <= max(sizes)  # contiguous, non-increasing tail
             assert all(sizes[i] >= sizes[i + 1] for i in range(world - 1))
+
+
+def test_bucket_complement_covers_the_gradient_buffer_exactly_once():
+    """The overlapped data-parallel step all-reduces the ranges each backward part finished, then `uncovered_ranges`:
+    together they must tile [0, n) exactly once (a gap would leave gradients un-averaged, an overlap would average twice)."""
+    from baddiffusion_b200.train import uncovered_ranges
+
+    n = 1000
+    for covered in ([], [(0, n)], [(100, 300), (300, 450), (700, 900)], [(700, 900), (100, 300)], [(0, 10), (990, n)]):
+        pieces = sorted(list(covered) + uncovered_ranges(covered, n))
+        assert pieces[0][0] == 0 and pieces[-1][1] == n
+        assert all(a[1] == b[0] for a, b in zip(pieces, pieces[1:]))
+        assert all(lo < hi for lo, hi in pieces)
