@@ -338,8 +338,9 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
             "data": "synthetic",
-            "config": {"workload": "DDPM-CIFAR10-32 poisoned train step (BASELINE configs[1]; N>1: configs[2])",
-                       "model": "UNet2DModel google/ddpm-cifar10-32 architecture, 35.7M params, random init",
+            "config": {"workload": "DDPM-CIFAR10-32 poisoned train step (BASELINE configs[1]; N>1: configs[2]): p_losses_diffuser "
+                                   "fwd/bwd over the google/ddpm-cifar10-32 UNet2DModel topology (35.7 M parameters, random init) "
+                                   "+ clip + Adam, synthetic 3x32x32",
                        "per_gpu_batch": B, "global_batch": B * world, "poison_rate": 0.1, "trigger": "BOX_14",
                        "target": "HAT", "precision": "fp16 operands, fp32 accumulate/master/GroupNorm/softmax, loss scaling",
                        "l2": "working set (activations+grads, >2 GB/step) exceeds the 126 MB L2; no explicit flush",
