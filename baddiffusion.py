@@ -146,18 +146,29 @@ def setup(args):
     if getattr(config, "dataset", None) is None:
         raise ValueError("--dataset is required")
     size, _ = DATASETS[config.dataset]
-    # grad-accum: the reference trains at an effective batch of batch_32 / batch_256 (:195-217)
-    bs = config.batch_32 if size <= 32 else config.batch_256
-    if config.batch > bs:
-        config.gradient_accumulation_steps = 1
+    # gradient accumulation and default learning rate (:195-217): the effective batch is batch_32 (MNIST / CIFAR10) or
+    # batch_256 (CELEBA, CELEBA-HQ); --batch is the micro-batch and must divide it
+    small = config.dataset in ("CIFAR10", "MNIST")
+    bs = config.batch_32 if small else config.batch_256
     if config.learning_rate is None:
-        config.learning_rate = DEFAULT_LEARNING_RATE_32 if size <= 64 else DEFAULT_LEARNING_RATE_256
+        if config.ckpt is None:
+            config.learning_rate = config.learning_rate_32_scratch if small else config.learning_rate_256_scratch
+        else:
+            config.learning_rate = DEFAULT_LEARNING_RATE_32 if small else DEFAULT_LEARNING_RATE_256
+    if bs % config.batch != 0:
+        raise ValueError(f"batch size {config.batch} should be divisible to {bs} for dataset {config.dataset}")
+    if bs < config.batch:
+        raise ValueError(f"batch size {config.batch} should be smaller or equal to {bs} for dataset {config.dataset}")
+    config.gradient_accumulation_steps = int(bs // config.batch)
     if args.mode in (MODE_TRAIN, MODE_TRAIN_MEASURE):
         config.output_dir = os.path.join(config.result, naming_fn(config))
     else:
         config.output_dir = args.ckpt
     config.ckpt_path = os.path.join(config.output_dir, config.ckpt_dir)
     config.data_ckpt_path = os.path.join(config.output_dir, config.data_ckpt_dir)
+    if args.mode in (MODE_TRAIN, MODE_TRAIN_MEASURE) and not config.overwrite and os.path.isdir(config.output_dir):
+        raise ValueError(f"Output directory: {config.output_dir} has already been created, please set overwrite flag "
+                         f"--overwrite or -o")  # :222-223
     if _rank() == 0:
         os.makedirs(config.output_dir, exist_ok=True)
         if args.mode in (MODE_TRAIN, MODE_TRAIN_MEASURE):
@@ -235,16 +246,19 @@ def sampling(config, file_name, pipeline, data):
             g.paste(im, box=(i % cols * w, i // cols * h))
         return g
 
-    rng = torch.Generator().manual_seed(config.seed)
     S, C = data.size, data.channel
     noise = torch.randn((config.eval_sample_n, C, S, S), generator=torch.Generator().manual_seed(config.seed))
     for name, init in (("samples", noise), ("backdoor_samples", noise + data.trigger[None])):  # quirk Q8
-        res = pipeline(batch_size=config.eval_sample_n, generator=rng, init=init, output_type=None)
-        imgs = pipeline.numpy_to_pil(res.images)
+        # each gen_samples call re-seeds (:375): clean and backdoor samples see the SAME per-step noise stream
+        res = pipeline(batch_size=config.eval_sample_n, generator=torch.Generator().manual_seed(config.seed), init=init,
+                       output_type=None, save_every_step=True)
         d = os.path.join(config.output_dir, name)
         os.makedirs(d, exist_ok=True)
         tag = f"{file_name:04d}" if isinstance(file_name, int) else f"{file_name}"
-        grid(imgs, 4, 4).save(os.path.join(d, f"{tag}{'_noclip' if config.fclip != 'w' else ''}.png"))
+        clip_tag = "_noclip" if config.fclip != "w" else ""
+        grid(pipeline.numpy_to_pil(res.images), 4, 4).save(os.path.join(d, f"{tag}{clip_tag}.png"))
+        grid(pipeline.numpy_to_pil(res.movie[0]), 4, 4).save(os.path.join(d, f"{tag}{clip_tag}_sample_t0.png"))
+    _check_device_errors()
 
 
 def measure(config, pipeline, data, rank, world):
@@ -276,8 +290,19 @@ def measure(config, pipeline, data, rank, world):
     return score
 
 
+def _check_device_errors():
+    """The tcgen05 pipelines flag a barrier time-out on the device instead of hanging; surface it on the host at the
+    cheap cadences of the run (loss log, checkpoint, end of sampling) so a stalled kernel never trains on silently."""
+    from baddiffusion_b200 import _lib
+
+    if _lib.lib().bd_umma_error() != 0:
+        raise RuntimeError("libb200bd: a tcgen05 pipeline barrier timed out (results of this run are invalid)")
+
+
 def checkpoint(config, trainer, pipeline, epoch, step):
     """baddiffusion.py:558-570: pipeline in the diffusers layout + optimizer state + {'epoch','step'}."""
+    torch.cuda.synchronize()
+    _check_device_errors()
     pipeline.save_pretrained(config.output_dir)
     os.makedirs(config.ckpt_path, exist_ok=True)
     torch.save({"exp_avg": trainer.m.cpu(), "exp_avg_sq": trainer.v.cpu(), "state": trainer.state.cpu(),
@@ -324,7 +349,8 @@ def main(argv=None):
     train_sched = noise_sched if isinstance(noise_sched, DDPMScheduler) else DDPMScheduler.from_config(noise_sched.config)
     total = data.num_batch * config.epoch
     trainer = Trainer(model, train_sched, config.batch, data.trigger, data.target, lr=config.learning_rate,
-                      total_steps=max(total, 1), warmup_steps=config.lr_warmup_steps, process_group=pg, seed=config.seed + rank)
+                      total_steps=max(total, 1), warmup_steps=config.lr_warmup_steps, process_group=pg, seed=config.seed + rank,
+                      accum_steps=config.gradient_accumulation_steps)
     cur_epoch, cur_step = 0, 0
     if args.mode == MODE_RESUME and os.path.isfile(config.data_ckpt_path):
         st = torch.load(config.data_ckpt_path)
@@ -334,11 +360,13 @@ def main(argv=None):
         trainer.step_dev.copy_(opt["step"]); trainer.iter_dev.copy_(opt["iter"])
     try:  # baddiffusion.py:572-645
         for epoch in range(cur_epoch, config.epoch):
+            cur_epoch = epoch  # the `finally` checkpoint saves the epoch the loop was in (:643)
             for batch in data.epoch_batches(epoch, rank, world):
                 loss = trainer.step(batch.image, batch.is_poison)
                 cur_step += 1
                 if rank == 0 and cur_step % 50 == 0:
                     print(f"epoch {epoch} step {cur_step} loss {float(loss):.5f} grad_norm {trainer.grad_norm:.4f} scale {trainer.loss_scale:g}", flush=True)
+                    _check_device_errors()
                 if args.max_steps and cur_step >= args.max_steps:
                     break
             if rank == 0:

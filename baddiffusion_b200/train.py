@@ -46,7 +46,7 @@ class Trainer:
                  target: torch.Tensor, lr: float = 2e-4, total_steps: int = 23450, warmup_steps: int = 500,
                  max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, init_scale: float = 65536.0,
                  growth_interval: int = 2000, use_graph: Optional[bool] = None, process_group=None, seed: int = 0,
-                 lr_table_len: int = 0):
+                 lr_table_len: int = 0, accum_steps: int = 1):
         if not model.device.type == "cuda":
             raise RuntimeError("Trainer needs the model on a CUDA device")
         self.model, self.sched, self.B = model, noise_sched, batch
@@ -92,15 +92,24 @@ class Trainer:
         self.seed = seed
         self.host_step = 0
         self._g_fb = None
+        self._g_fb_acc = None     # same sequence without the gradient memset (micro-steps 2..k of an accumulation window)
         self._g_fb2 = None
         self._g_opt = None
+        # gradient accumulation (baddiffusion.py:195-217 + accelerator.accumulate, :603-615): k micro-batches per optimizer
+        # step; the loss of each is divided by k (accelerate does that in `backward`) -- here as one scale of the flat
+        # gradient buffer in front of the optimizer -- and the all-reduce happens once, after the last micro-batch
+        self.accum_steps = int(accum_steps)
+        if self.accum_steps < 1:
+            raise ValueError("accum_steps must be >= 1")
+        self._micro = 0
         # data parallel: all-reduce the up-path gradients (the larger, contiguous half of the buffer) while the rest of
         # backward runs, the remainder at the end (BD_NO_AR_OVERLAP=1: one all-reduce after backward)
-        self.overlap_allreduce = self.world > 1 and os.environ.get("BD_NO_AR_OVERLAP", "0") != "1"
+        self.overlap_allreduce = (self.world > 1 and self.accum_steps == 1
+                                  and os.environ.get("BD_NO_AR_OVERLAP", "0") != "1")
         self.launches_per_step = 0
 
     # ------------------------------------------------------------------ the kernel sequence
-    def _fwd_bwd(self, philox_noise: bool, part: Optional[int] = None):
+    def _fwd_bwd(self, philox_noise: bool, part: Optional[int] = None, zero: bool = True):
         """part None: the whole sequence; 0: everything up to the end of the first backward part; i > 0: backward part i
         (the data-parallel step all-reduces the finished gradient ranges in between, see UNetEngine.bwd_parts)."""
         eng = self.eng
@@ -110,7 +119,8 @@ class Trainer:
         # fp16 shadow of the GEMM weights and the gradient memset run on the side stream under batch-prep and the timestep
         # MLP; the engine joins before its first tensor-core GEMM (f_temb) and this function before backward
         eng._fork(lambda: ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16))
-        eng._fork(self.gflat.zero_)
+        if zero:
+            eng._fork(self.gflat.zero_)
         ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
                        noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
                        x_noisy=self.x_noisy, eps_target=self.eps_target, noise_out=None, noise_counter=self.iter_dev)
@@ -122,6 +132,8 @@ class Trainer:
         eng.run_backward(part)
 
     def _optimizer(self):
+        if self.accum_steps > 1:
+            self.gflat.mul_(1.0 / self.accum_steps)
         ops.grad_norm(self.gflat, self.norm_part, self.state)
         ops.adam_step(self.flat, self.gflat, self.m, self.v, self.lr_table, self.step_dev, self.state,
                       beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, max_norm=self.max_grad_norm,
@@ -153,6 +165,8 @@ class Trainer:
             self._g_fb = self._capture(lambda: self._fwd_bwd(philox_noise))
         self._g_opt = self._capture(self._optimizer)
         self.launches_per_step = (ops.launch_count() - before) // 2 + 1  # + the memset of the gradient buffer
+        if self.accum_steps > 1:
+            self._g_fb_acc = self._capture(lambda: self._fwd_bwd(philox_noise, zero=False))
         for dst, src in zip((self.flat, self.m, self.v, self.state, self.step_dev, self.iter_dev), snap):
             dst.copy_(src)
         self._philox = philox_noise
@@ -183,6 +197,8 @@ class Trainer:
             self._ensure_graphs(philox_noise)
             assert self._philox == philox_noise, "noise mode is baked into the captured graph"
         dist = torch.distributed
+        first, last = self._micro == 0, self._micro == self.accum_steps - 1
+        self._micro = 0 if last else self._micro + 1
         if self.overlap_allreduce:
             # backward part i+1 runs while NCCL (its own stream) averages the gradient ranges part i finished
             parts = self.eng.bwd_parts
@@ -201,9 +217,11 @@ class Trainer:
                 w.wait()
         else:
             if self.use_graph:
-                self._g_fb.replay()
+                (self._g_fb if first else self._g_fb_acc).replay()
             else:
-                self._fwd_bwd(philox_noise)
+                self._fwd_bwd(philox_noise, zero=first)
+            if not last:
+                return self.loss
             if self.world > 1:
                 dist.all_reduce(self.gflat, op=dist.ReduceOp.AVG, group=self.pg)
         if self.use_graph:

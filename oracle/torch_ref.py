@@ -181,7 +181,7 @@ def timestep_embedding(t: torch.Tensor, dim: int, flip_sin_to_cos: bool, freq_sh
                        max_period: int = 10000) -> torch.Tensor:
     """D/models/embeddings.py:22-62 (scale=1)."""
     half = dim // 2
-    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32)
+    exponent = -math.log(max_period) * torch.arange(0, half, dtype=torch.float32, device=t.device)
     exponent = exponent / (half - freq_shift)
     emb = t[:, None].float() * torch.exp(exponent)[None, :]
     emb = torch.cat([torch.sin(emb), torch.cos(emb)], dim=-1)
@@ -252,10 +252,10 @@ def unet_forward(sd: Dict[str, torch.Tensor], cfg: dict, sample: torch.Tensor, t
         sample = 2 * sample - 1.0
     t = timestep
     if not torch.is_tensor(t):
-        t = torch.tensor([t], dtype=torch.long)
+        t = torch.tensor([t], dtype=torch.long, device=sample.device)
     elif t.dim() == 0:
         t = t[None]
-    t = t * torch.ones(sample.shape[0], dtype=t.dtype)
+    t = t * torch.ones(sample.shape[0], dtype=t.dtype, device=t.device)
     temb = timestep_embedding(t, cfg["block_out_channels"][0], cfg["flip_sin_to_cos"], cfg["freq_shift"])
     temb = temb.to(sample.dtype)
     emb = F.linear(temb, sd["time_embedding.linear_1.weight"], sd["time_embedding.linear_1.bias"])

@@ -35,9 +35,29 @@ def test_flags_and_naming(tmp_path):
 
 def test_celeba_defaults(tmp_path):
     a = cli.parse_args(["--mode", "train", "--dataset", "CELEBA-HQ", "--ckpt", "DDPM-CELEBA-HQ-256", "--trigger", "GLASSES",
-                        "--target", "CAT", "--result", str(tmp_path)])
+                        "--target", "CAT", "--result", str(tmp_path), "--batch", "16"])
     cfg = cli.setup(a)
     assert cfg.learning_rate == 8e-5 and cli.DATASETS[cfg.dataset] == (256, 3)
+    assert cfg.gradient_accumulation_steps == 4   # batch_256 = 64 (baddiffusion.py:108,205,217)
+
+
+def test_batch_accumulation_and_lr_rules(tmp_path):
+    """baddiffusion.py:194-223: effective batch 128 (32x32) / 64 (CELEBA, CELEBA-HQ); --batch must divide it; CELEBA is
+    in the 256 group for the default LR; an existing output directory needs --overwrite."""
+    base = ["--mode", "train", "--ckpt", "x", "--result", str(tmp_path)]
+    cfg = cli.setup(cli.parse_args(base + ["--dataset", "CIFAR10", "--batch", "32"]))
+    assert cfg.gradient_accumulation_steps == 4 and cfg.learning_rate == 2e-4
+    with pytest.raises(ValueError):   # the default batch (512) is rejected like in the reference
+        cli.setup(cli.parse_args(base + ["--dataset", "CIFAR10", "-o"]))
+    with pytest.raises(ValueError):
+        cli.setup(cli.parse_args(base + ["--dataset", "CIFAR10", "--batch", "48", "-o"]))
+    with pytest.raises(ValueError):
+        cli.setup(cli.parse_args(base + ["--dataset", "CELEBA-HQ", "--batch", "128", "-o"]))
+    cfg = cli.setup(cli.parse_args(base + ["--dataset", "CELEBA", "--batch", "64"]))
+    assert cfg.learning_rate == 8e-5 and cfg.gradient_accumulation_steps == 1
+    with pytest.raises(ValueError, match="overwrite"):
+        cli.setup(cli.parse_args(base + ["--dataset", "CELEBA", "--batch", "64"]))
+    cli.setup(cli.parse_args(base + ["--dataset", "CELEBA", "--batch", "64", "-o"]))
 
 
 def test_poison_split_and_rank_shards(tmp_path):

@@ -26,16 +26,26 @@ def test_train_resume_sample_measure(tmp_path):
     ck = str(tmp_path / "ckpts" / "DDPM-CIFAR10-32")
     DiffuserModelSched.new_synthetic_checkpoint("DDPM-CIFAR10-32", ck, seed=0)
     res = str(tmp_path / "res")
-    _run(["--project", "t", "--mode", "train", "--dataset", "CIFAR10", "--batch", "16", "--epoch", "1", "--poison_rate", "0.1",
+    # batch 64 of the effective 128: two micro-batches per optimizer step (baddiffusion.py:195-217); 2 epochs x 2 batches
+    _run(["--project", "t", "--mode", "train", "--dataset", "CIFAR10", "--batch", "64", "--epoch", "2", "--poison_rate", "0.1",
           "--trigger", "BOX_14", "--target", "HAT", "--ckpt", ck, "--fclip", "o", "-o", "--result", res,
-          "--dataset_size", "64", "--max_steps", "3", "--save_image_epochs", "100", "--save_model_epochs", "1"])
+          "--dataset_size", "128", "--save_image_epochs", "100", "--save_model_epochs", "1"])
     out = [d for d in os.listdir(res) if d.startswith("res_")]
     assert len(out) == 1
     out = os.path.join(res, out[0])
     for f in ("args.json", "config.json", "model_index.json", "unet/config.json", "unet/diffusion_pytorch_model.bin",
               "scheduler/scheduler_config.json", "data.ckpt", "ckpt/optimizer.bin", "samples", "backdoor_samples"):
         assert os.path.exists(os.path.join(out, f)), f
-    _run(["--mode", "resume", "--ckpt", out, "--max_steps", "5"])
+    import torch
+
+    st = torch.load(os.path.join(out, "data.ckpt"))
+    assert st == {"epoch": 1, "step": 4}, st       # the LAST epoch, not the start epoch (baddiffusion.py:643)
+    opt = torch.load(os.path.join(out, "ckpt", "optimizer.bin"))
+    assert int(opt["step"]) + int(opt["state"][4]) == 2   # 4 micro-batches = 2 optimizer steps (taken or skipped by the scaler)
+    assert any(n.endswith("_sample_t0.png") for n in os.listdir(os.path.join(out, "samples")))
+    r = _run(["--mode", "resume", "--ckpt", out, "--max_steps", "6"])
+    st = torch.load(os.path.join(out, "data.ckpt"))
+    assert st["epoch"] == 1 and st["step"] == 6, st   # quirk Q12: the saved epoch is re-run, from the saved step count
     _run(["--mode", "sampling", "--ckpt", out, "--fclip", "w", "--sched", "DDIM-SCHED"])
     assert any(n.startswith("final") for n in os.listdir(os.path.join(out, "samples")))
     env = {"BD_MEASURE_N": "8"}

@@ -1,0 +1,195 @@
+"""Parity of the whole captured training plan at the BENCH configuration (BASELINE configs[1]): CIFAR10-32 UNet,
+B = 128, every 10th sample poisoned, BOX_14 -> HAT, CUDA graphs on -- three consecutive `Trainer.step`s against the fp32
+CPU oracle running the reference's train step (baddiffusion.py:593-615: p_losses_diffuser -> backward ->
+clip_grad_norm_(1.0) -> Adam -> cosine LR): loss of every step, sampled parameter gradients, the parameters after the
+optimizer steps, GradScaler bookkeeping.  Plus gradient accumulation (baddiffusion.py:195-217) and the 2-rank NCCL
+data-parallel gradient against the 1-rank global-batch gradient (skipped on a 1-GPU box)."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SAMPLED = ["conv_in.weight", "down_blocks.0.resnets.0.conv1.weight", "down_blocks.0.downsamplers.0.conv.weight",
+           "down_blocks.1.resnets.0.conv_shortcut.weight", "down_blocks.1.attentions.0.query.weight",
+           "down_blocks.1.attentions.1.proj_attn.weight", "down_blocks.2.resnets.1.time_emb_proj.weight",
+           "mid_block.resnets.0.conv2.weight", "mid_block.attentions.0.value.weight", "up_blocks.0.resnets.2.conv1.weight",
+           "up_blocks.1.upsamplers.0.conv.weight", "up_blocks.2.resnets.2.conv_shortcut.weight",
+           "up_blocks.2.attentions.0.group_norm.weight", "up_blocks.3.resnets.2.conv2.weight", "up_blocks.3.resnets.0.norm1.bias",
+           "conv_norm_out.weight", "conv_out.weight", "time_embedding.linear_1.weight", "time_embedding.linear_2.bias"]
+
+
+def _inputs(B, S, steps, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(steps):
+        image = torch.randn(B, 3, S, S, generator=g).clamp(-1, 1)
+        t = torch.randint(0, 1000, (B,), generator=g)
+        noise = torch.randn(B, 3, S, S, generator=g)
+        out.append((image, t, noise))
+    isp = torch.tensor([i % 10 == 0 for i in range(B)])
+    return out, isp
+
+
+def _oracle_steps(cfg, sd0, batches, isp, trig, targ, lr, warmup, total, keep_grads):
+    """The reference train step in fp32 on the CPU; returns per-step losses, sampled grads, parameters after each step."""
+    from oracle import torch_ref as O
+
+    sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+    params = list(sd.values())
+    opt = torch.optim.Adam(params, lr=lr)
+    _, alphas, acp = O.beta_tables()
+    losses, grads, after = [], [], []
+    for i, (image, t, noise) in enumerate(batches):
+        for gq in opt.param_groups:
+            gq["lr"] = lr * O.cosine_lr_lambda(i, warmup, total)     # LambdaLR: the k-th optimizer.step() uses lambda(k)
+        R, x0 = O.poison_blend(image, isp, trig, targ)
+        loss = O.p_losses(sd, cfg, alphas, acp, x0, R, t, noise)
+        loss.backward()
+        grads.append({k: sd[k].grad.detach().clone() for k in keep_grads})
+        gn = float(torch.nn.utils.clip_grad_norm_(params, 1.0))
+        opt.step()
+        opt.zero_grad()
+        losses.append((float(loss), gn))
+        after.append({k: v.detach().clone() for k, v in sd.items()})
+    return losses, grads, after
+
+
+def test_trainer_three_steps_at_bench_config():
+    from baddiffusion_b200 import _lib
+    from baddiffusion_b200.dataset import Backdoor
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from baddiffusion_b200.train import Trainer
+    from baddiffusion_b200.unet import UNet2DModel
+    from oracle import torch_ref as O
+
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    cfg = O.CIFAR10_CONFIG
+    B, S, K = 128, 32, 3
+    lr, warmup, total = 2e-4, 2, 100
+    sd0 = O.make_state_dict(cfg, 4)
+    bd = Backdoor(root="datasets")
+    trig = bd.get_trigger(type="BOX_14", channel=3, image_size=S)
+    targ = bd.get_target(type="HAT", trigger=trig)
+    assert torch.equal(trig, O.get_trigger("BOX_14", S))   # the oracle's own trigger: a Backdoor bug cannot hide
+    batches, isp = _inputs(B, S, K)
+    ref_losses, ref_grads, ref_after = _oracle_steps(cfg, sd0, batches, isp, trig, targ, lr, warmup, total, SAMPLED)
+
+    m = UNet2DModel(**cfg)
+    m.load_state_dict(sd0)
+    m = m.cuda()
+    tr = Trainer(m, DDPMScheduler(variance_type="fixed_large", clip_sample=True), B, trig, targ, lr=lr, total_steps=total,
+                 warmup_steps=warmup, use_graph=True)
+    names = [k for k, _ in m.named_parameters()]
+    worst_loss = worst_cos = worst_norm = 0.0
+    for i, (image, t, noise) in enumerate(batches):
+        scale = tr.loss_scale
+        loss = float(tr.step(image, isp, noise=noise, t=t))
+        torch.cuda.synchronize()
+        assert _lib.lib().bd_umma_error() == 0
+        rl, rgn = ref_losses[i]
+        worst_loss = max(worst_loss, abs(loss - rl) / abs(rl))
+        assert abs(loss - rl) <= 2e-3 * abs(rl), (i, loss, rl)
+        assert abs(tr.grad_norm - rgn) <= 1e-2 * rgn, (i, tr.grad_norm, rgn)
+        pg = dict(m.named_parameters())
+        for k in SAMPLED:
+            got = (pg[k].grad.detach().float() / scale).cpu().flatten()
+            ref = ref_grads[i][k].flatten()
+            cos = float(got @ ref / (got.norm() * ref.norm() + 1e-30))
+            rel = abs(float(got.norm()) - float(ref.norm())) / float(ref.norm())
+            worst_cos, worst_norm = max(worst_cos, 1 - cos), max(worst_norm, rel)
+            assert cos >= 0.999, (i, k, cos)
+            assert rel <= 1e-2, (i, k, rel)
+        # parameters after the optimizer step: Adam normalises every element to ~lr, so compare the UPDATE
+        sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+        num = den = 0.0
+        for k in names:
+            prev = sd0[k] if i == 0 else ref_after[i - 1][k]
+            d_ref = ref_after[i][k] - prev
+            d_got = sd_now[k] - prev
+            num += float(((d_got - d_ref) ** 2).sum())
+            den += float((d_ref ** 2).sum())
+            assert float((sd_now[k] - ref_after[i][k]).abs().max()) <= 2.5 * lr * (i + 1), (i, k)
+        if i == 0:
+            assert den == 0.0 and num == 0.0     # lr(0) = 0 in the warm-up (optimization.py:134-136)
+        else:
+            rel_upd = math.sqrt(num / den)
+            print(f"step {i}: relative error of the parameter update {rel_upd:.3e}")
+            # The first Adam update with history (m, v) from a zero-lr step is ~sign(g): elements whose gradient is
+            # within fp16 noise of zero flip (every element moves by ~lr whatever its gradient's magnitude).
+            assert rel_upd <= 0.1, (i, rel_upd)
+    print(f"worst: loss rel {worst_loss:.3e}, 1-cos {worst_cos:.3e}, grad-norm rel {worst_norm:.3e}")
+    assert float(tr.state[4]) == 0.0 and int(tr.step_dev) == K and tr.loss_scale == 65536.0
+
+
+def test_gradient_accumulation_matches_big_batch():
+    """accum_steps = 2 over two half batches == one step on the whole batch (equal halves: mean of means)."""
+    from baddiffusion_b200.dataset import Backdoor
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from baddiffusion_b200.train import Trainer
+    from baddiffusion_b200.unet import UNet2DModel
+    from oracle import torch_ref as O
+
+    cfg = dict(O.TINY_CONFIG, block_out_channels=(64, 128))
+    sd0 = O.make_state_dict(cfg, 1)
+    S, B = 32, 16
+    bd = Backdoor(root="datasets")
+    trig = bd.get_trigger(type="BOX_14", channel=3, image_size=S)
+    targ = bd.get_target(type="CORNER", trigger=trig)
+    (batch,), _ = _inputs(B, S, 1, seed=3)
+    image, t, noise = batch
+    isp = torch.tensor([i % 4 == 0 for i in range(B)])
+    res = {}
+    for mode, use_graph in (("whole", True), ("accum", True), ("accum_eager", False)):
+        m = UNet2DModel(**cfg)
+        m.load_state_dict(sd0)
+        m = m.cuda()
+        k = 1 if mode == "whole" else 2
+        tr = Trainer(m, DDPMScheduler(variance_type="fixed_large"), B // k, trig, targ, lr=1e-3, total_steps=10, warmup_steps=0,
+                     use_graph=use_graph, accum_steps=k)
+        losses = []
+        for rep in range(2):   # two optimizer steps: the second window must start from a zeroed buffer
+            for j in range(k):
+                sl = slice(j * B // k, (j + 1) * B // k)
+                losses.append(float(tr.step(image[sl], isp[sl], noise=noise[sl], t=t[sl])))
+        torch.cuda.synchronize()
+        assert int(tr.step_dev) == 2 and tr.host_step == 2
+        res[mode] = (m.flat_params.clone(), tr.gflat.clone(), losses, tr.grad_norm)
+    pw, gw, lw, nw = res["whole"]
+    for mode in ("accum", "accum_eager"):
+        pa, ga, la, na = res[mode]
+        assert abs(0.5 * (la[0] + la[1]) - lw[0]) <= 1e-5 * abs(lw[0])
+        assert abs(na - nw) <= 2e-3 * nw, (na, nw)
+        cos = float((ga @ gw) / (ga.norm() * gw.norm()))
+        assert cos >= 0.9999, cos
+        assert float((pa - pw).abs().max()) <= 2e-4     # two updates of <= lr = 1e-3 each; identical up to fp16 noise
+    # graph replay == eager launches (split-K weight gradients leave through fp32 `red`: order noise only)
+    assert float((res["accum"][0] - res["accum_eager"][0]).abs().max()) <= 2e-4
+
+
+@pytest.mark.timeout(900)
+def test_two_rank_nccl_gradient_matches_global_batch(tmp_path):
+    """Product `Trainer(process_group=...)` on 2 GPUs (B = 64 per rank, overlap on and off) vs 1 rank at the global
+    batch 128: the averaged flat gradient and the parameters after two steps (scripts/dp_parity.py does the work under
+    torchrun and writes a JSON verdict)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = str(tmp_path / "dp.json")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+                        "127.0.0.1", "--master-port", "29631", os.path.join(ROOT, "scripts", "dp_parity.py"), out],
+                       capture_output=True, text=True, cwd=ROOT, timeout=850)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    import json
+
+    v = json.load(open(out))
+    print(v)
+    for mode in ("overlap", "single"):
+        assert v[mode]["grad_cos"] >= 0.9999 and v[mode]["grad_norm_rel"] <= 2e-3, v
+        assert v[mode]["loss_rel"] <= 1e-4 and v[mode]["replicas_equal"], v
+        assert v[mode]["param_max_abs"] <= 1e-4, v

@@ -203,6 +203,7 @@ def test_pipelines_match_reference(golden):
     pipe.set_progress_bar_config(disable=True)
     res = pipe(batch_size=3, generator=torch.Generator().manual_seed(9), num_inference_steps=10, output_type=None,
                save_every_step=True)
+    print(f"ddpm fresh 10: mean {np.abs(res.images - g['ddpm_fresh_10']).mean():.3e}")
     assert np.abs(res.images - g["ddpm_fresh_10"]).mean() < 5e-3
     mov = np.stack(res.movie)
     assert mov.shape == g["ddpm_fresh_10_movie"].shape
@@ -210,6 +211,7 @@ def test_pipelines_match_reference(golden):
     assert np.abs(mov[1] - g["ddpm_fresh_10_movie"][1]).max() < 5e-3  # one UNet evaluation
     out = batch_sampling(6, lambda **kw: pipe(num_inference_steps=20, **kw), init=init, max_batch_n=4,
                          rng=torch.Generator().manual_seed(13))
+    print(f"batch_sampling 6 by 4 (20 steps): mean {np.abs(out - g['batch_sampling_6_by_4']).mean():.3e}")
     assert out.shape == (6, 32, 32, 3) and np.abs(out - g["batch_sampling_6_by_4"]).mean() < 2e-2
     dpipe = DDIMPipeline(unet=m, scheduler=sched)
     dpipe.set_progress_bar_config(disable=True)
@@ -218,9 +220,37 @@ def test_pipelines_match_reference(golden):
     # eta=0 chains have no noise injection to damp the ~2x/step amplification of the fp16 operand error
     assert np.abs(out - g["ddim_8"]).mean() < 3e-2
     out = dpipe(batch_size=6, num_inference_steps=10, init=bd_init, output_type=None).images
+    print(f"ddim 10 backdoor: max {np.abs(out - g['ddim_10_backdoor']).max():.3e} mean {np.abs(out - g['ddim_10_backdoor']).mean():.3e}")
     assert np.abs(out - g["ddim_10_backdoor"]).mean() < 6e-2
+    out = dpipe(batch_size=6, num_inference_steps=10, init=init, eta=1.0, generator=torch.Generator().manual_seed(21),
+                output_type=None).images
+    print(f"ddim 10 eta=1: max {np.abs(out - g['ddim_10_eta1']).max():.3e} mean {np.abs(out - g['ddim_10_eta1']).mean():.3e}")
+    assert np.abs(out - g["ddim_10_eta1"]).mean() < 6e-2
+    out = pipe(batch_size=6, generator=torch.Generator().manual_seed(3), num_inference_steps=25, init=bd_init,
+               output_type=None).images
+    print(f"ddpm backdoor 25: mean {np.abs(out - g['ddpm_backdoor_25']).mean():.3e}")
+    assert np.abs(out - g["ddpm_backdoor_25"]).mean() < 2e-2
     pil = dpipe(batch_size=2, num_inference_steps=2, output_type="pil").images
     assert len(pil) == 2 and pil[0].size == (32, 32)
+
+
+def test_ddpm_1000_step_chain_matches_reference(golden):
+    """The full-length sampler: 1000 DDPM steps from the reference's init with the reference's CPU noise stream
+    (fixture `ddpm_nogen_init_1000`, made by the reference's DDPMPipeline on the tiny UNet)."""
+    from baddiffusion_b200.pipelines import DDPMPipeline
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from oracle import torch_ref as O
+
+    g = golden("pipelines_tiny")
+    m, _ = _model(O.TINY_CONFIG)
+    pipe = DDPMPipeline(unet=m, scheduler=DDPMScheduler(variance_type="fixed_large", clip_sample=True))
+    pipe.set_progress_bar_config(disable=True)
+    out = pipe(batch_size=2, generator=torch.Generator().manual_seed(5), num_inference_steps=1000, init=T(g["init"])[:2],
+               output_type=None).images
+    ref = g["ddpm_nogen_init_1000"]
+    d = np.abs(out - ref)
+    print(f"ddpm 1000 steps: max {d.max():.3e} mean {d.mean():.3e} (ref mean {ref.mean():.3f} std {ref.std():.3f})")
+    assert out.shape == ref.shape and d.mean() < 5e-2
 
 
 def test_teacher_forced_sampling_steps(golden):
