@@ -95,8 +95,8 @@ def test_trainer_three_steps_at_bench_config():
         assert _lib.lib().bd_umma_error() == 0
         rl, rgn = ref_losses[i]
         worst_loss = max(worst_loss, abs(loss - rl) / abs(rl))
-        assert abs(loss - rl) <= 2e-3 * abs(rl), (i, loss, rl)
-        assert abs(tr.grad_norm - rgn) <= 1e-2 * rgn, (i, tr.grad_norm, rgn)
+        assert abs(loss - rl) <= 2e-4 * abs(rl), (i, loss, rl)   # measured 3.4e-5
+        assert abs(tr.grad_norm - rgn) <= 2e-3 * rgn, (i, tr.grad_norm, rgn)
         pg = dict(m.named_parameters())
         for k in SAMPLED:
             got = (pg[k].grad.detach().float() / scale).cpu().flatten()
@@ -104,8 +104,8 @@ def test_trainer_three_steps_at_bench_config():
             cos = float(got @ ref / (got.norm() * ref.norm() + 1e-30))
             rel = abs(float(got.norm()) - float(ref.norm())) / float(ref.norm())
             worst_cos, worst_norm = max(worst_cos, 1 - cos), max(worst_norm, rel)
-            assert cos >= 0.999, (i, k, cos)
-            assert rel <= 1e-2, (i, k, rel)
+            assert cos >= 0.99999, (i, k, cos)     # measured worst 1 - cos = 7.2e-7
+            assert rel <= 2e-3, (i, k, rel)        # measured worst 3.9e-4
         # parameters after the optimizer step: Adam normalises every element to ~lr, so compare the UPDATE
         sd_now = {k: v.detach().cpu() for k, v in m.state_dict().items()}
         num = den = 0.0
@@ -123,7 +123,7 @@ def test_trainer_three_steps_at_bench_config():
             print(f"step {i}: relative error of the parameter update {rel_upd:.3e}")
             # The first Adam update with history (m, v) from a zero-lr step is ~sign(g): elements whose gradient is
             # within fp16 noise of zero flip (every element moves by ~lr whatever its gradient's magnitude).
-            assert rel_upd <= 0.1, (i, rel_upd)
+            assert rel_upd <= 2.5e-2, (i, rel_upd)    # measured 4.7e-3 on B200
     print(f"worst: loss rel {worst_loss:.3e}, 1-cos {worst_cos:.3e}, grad-norm rel {worst_norm:.3e}")
     assert float(tr.state[4]) == 0.0 and int(tr.step_dev) == K and tr.loss_scale == 65536.0
 
@@ -151,6 +151,7 @@ def test_gradient_accumulation_matches_big_batch():
         m.load_state_dict(sd0)
         m = m.cuda()
         k = 1 if mode == "whole" else 2
+        p_init = m.flat_params.clone()
         tr = Trainer(m, DDPMScheduler(variance_type="fixed_large"), B // k, trig, targ, lr=1e-3, total_steps=10, warmup_steps=0,
                      use_graph=use_graph, accum_steps=k)
         losses = []
@@ -160,17 +161,23 @@ def test_gradient_accumulation_matches_big_batch():
                 losses.append(float(tr.step(image[sl], isp[sl], noise=noise[sl], t=t[sl])))
         torch.cuda.synchronize()
         assert int(tr.step_dev) == 2 and tr.host_step == 2
-        res[mode] = (m.flat_params.clone(), tr.gflat.clone(), losses, tr.grad_norm)
-    pw, gw, lw, nw = res["whole"]
+        res[mode] = (m.flat_params.clone(), tr.gflat.clone(), losses, tr.grad_norm, p_init)
+    pw, gw, lw, nw, _ = res["whole"]
     for mode in ("accum", "accum_eager"):
-        pa, ga, la, na = res[mode]
+        pa, ga, la, na, _ = res[mode]
         assert abs(0.5 * (la[0] + la[1]) - lw[0]) <= 1e-5 * abs(lw[0])
         assert abs(na - nw) <= 2e-3 * nw, (na, nw)
         cos = float((ga @ gw) / (ga.norm() * gw.norm()))
         assert cos >= 0.9999, cos
-        assert float((pa - pw).abs().max()) <= 2e-4     # two updates of <= lr = 1e-3 each; identical up to fp16 noise
+        # Adam moves every element by ~lr whatever its gradient's size, so elements whose gradient is within fp16 noise
+        # of zero may flip sign (max-abs difference up to 2 * lr per step): compare the UPDATE in the 2-norm
+        rel = float((pa - pw).norm() / (pw - res["whole"][4]).norm())
+        print(f"[{mode}] relative difference of the two-step update vs whole-batch: {rel:.3e}")
+        assert rel <= 5e-2, rel
+        assert float((pa - pw).abs().max()) <= 4.5e-3
     # graph replay == eager launches (split-K weight gradients leave through fp32 `red`: order noise only)
-    assert float((res["accum"][0] - res["accum_eager"][0]).abs().max()) <= 2e-4
+    rel = float((res["accum"][0] - res["accum_eager"][0]).norm() / (res["accum"][0] - res["accum"][4]).norm())
+    assert rel <= 2e-2, rel
 
 
 @pytest.mark.timeout(900)
