@@ -44,6 +44,7 @@ _SIGS = {
     "bd_device_supported": (i32, []),
     "bd_launch_count": (u64, []),
     "bd_batch_prep": (i32, [vp] * 12 + [i32] * 5 + [u64, u64, vp, vp]),
+    "bd_batch_prep_u8": (i32, [vp] * 13 + [i32] * 5 + [u64, u64, vp, vp]),
     "bd_mse_workspace_floats": (sz, []),
     "bd_mse_fwd_bwd": (i32, [vp] * 6 + [sz, vp]),
     "bd_ddpm_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),

@@ -65,8 +65,14 @@ __device__ __forceinline__ float4 philox_normal4(uint64_t seed, uint64_t offset,
 // K11 batch-prep.  One thread = 4 consecutive elements of one sample (float4 I/O, HW % 4 == 0).
 // Algorithmic bytes / element: img 4 (+ noise 4) + x_noisy 4 + target 4 = 12..16 B.
 // ---------------------------------------------------------------------------------------------
+// U8 (dataset.py:120-136,288-315): `img` is the decoded uint8 NHWC batch; ToTensor (/255), util.normalize
+// (quirk Q7: / (1 - 0 + 1e-5), * 2, + -1; each op rounded separately like the reference's torch ops) and
+// RandomHorizontalFlip (per-sample decision drawn by the host, `flip`) happen on load, so the fp32 NCHW image tensor of
+// the reference's DataLoader never exists (image_out: optional copy of it = the reference's `image` key).
+template <bool U8>
 __global__ void __launch_bounds__(256) batch_prep_kernel(
-    const float* __restrict__ img, const uint8_t* __restrict__ is_poison, const float* __restrict__ trigger,
+    const void* __restrict__ img_any, const uint8_t* __restrict__ flip, float* __restrict__ image_out, int C, int H, int W,
+    const uint8_t* __restrict__ is_poison, const float* __restrict__ trigger,
     const float* __restrict__ target, const float* __restrict__ R_explicit, const float* __restrict__ noise,
     const int64_t* __restrict__ t, const float* __restrict__ alphas, const float* __restrict__ acp,
     float* __restrict__ x_noisy, float* __restrict__ eps_target, float* __restrict__ noise_out, int B, int CHW4,
@@ -83,7 +89,24 @@ __global__ void __launch_bounds__(256) batch_prep_kernel(
   const bool poison = is_poison ? (is_poison[b] != 0) : false;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < CHW4; i += gridDim.x * blockDim.x) {
     const size_t g = (size_t)b * CHW4 + i;
-    float4 im = reinterpret_cast<const float4*>(img)[g];
+    float4 im;
+    if (!U8) {
+      im = reinterpret_cast<const float4*>(img_any)[g];
+    } else {
+      // element index -> (c, h, w..w+3); W % 4 == 0 keeps the four elements in one image row
+      const int e0 = i * 4, w0 = e0 % W, h = (e0 / W) % H, c = e0 / (W * H);
+      const uint8_t* row = reinterpret_cast<const uint8_t*>(img_any) + ((size_t)b * H + h) * W * C + c;
+      const bool fl = flip && flip[b];
+      float v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int w = fl ? (W - 1 - (w0 + k)) : (w0 + k);
+        const float u = __fdiv_rn((float)row[(size_t)w * C], 255.0f);                  // transforms.ToTensor
+        v[k] = __fadd_rn(__fmul_rn(__fdiv_rn(u, 1.00001f), 2.0f), -1.0f);             // util.py:111 with vmin_in 0, vmax_in 1
+      }
+      im = make_float4(v[0], v[1], v[2], v[3]);
+      if (image_out) reinterpret_cast<float4*>(image_out)[g] = im;
+    }
     float4 e;
     if (noise) e = reinterpret_cast<const float4*>(noise)[g];
     else e = philox_normal4(seed, offset, g);
@@ -414,9 +437,29 @@ int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigg
   if (B == 0) return BD_OK;  // loss.py:288-289 (empty batch)
   int chw4 = (int)((size_t)C * H * W / 4);
   dim3 grid(ceil_div(chw4, 256) < 64 ? ceil_div(chw4, 256) : 64, B);
-  batch_prep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img, is_poison, trigger, target, R_explicit, noise, t,
-                                                           alphas, alphas_cumprod, x_noisy, eps_target, noise_out, B,
-                                                           chw4, seed, offset, noise_counter);
+  batch_prep_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(img, nullptr, nullptr, C, H, W, is_poison, trigger, target,
+                                                                  R_explicit, noise, t, alphas, alphas_cumprod, x_noisy,
+                                                                  eps_target, noise_out, B, chw4, seed, offset, noise_counter);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_batch_prep_u8(const uint8_t* img_nhwc, const uint8_t* flip, const uint8_t* is_poison, const float* trigger,
+                     const float* target, const float* noise, const int64_t* t, const float* alphas,
+                     const float* alphas_cumprod, float* x_noisy, float* eps_target, float* noise_out, float* image_out,
+                     int B, int C, int H, int W, int T, uint64_t seed, uint64_t offset, const int* noise_counter,
+                     void* stream) {
+  BD_CHECK_ARG(img_nhwc && t && alphas && alphas_cumprod && x_noisy && eps_target, "bd_batch_prep_u8: null pointer");
+  BD_CHECK_ARG(B >= 0 && C > 0 && H > 0 && W > 0 && T > 0, "bd_batch_prep_u8: bad shape");
+  BD_CHECK_ARG(W % 4 == 0, "bd_batch_prep_u8: W must be a multiple of 4");
+  BD_CHECK_ARG(!is_poison || (trigger && target), "bd_batch_prep_u8: trigger/target required");
+  if (B == 0) return BD_OK;
+  int chw4 = (int)((size_t)C * H * W / 4);
+  dim3 grid(ceil_div(chw4, 256) < 64 ? ceil_div(chw4, 256) : 64, B);
+  batch_prep_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(img_nhwc, flip, image_out, C, H, W, is_poison, trigger, target,
+                                                                 nullptr, noise, t, alphas, alphas_cumprod, x_noisy,
+                                                                 eps_target, noise_out, B, chw4, seed, offset, noise_counter);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -265,6 +265,9 @@ int conv3_supported(const Conv3Call& c) {
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
                   Conv3Params p, bool a_mn, dim3 grid, cudaStream_t st);
 int conv3w_launch_fwd(const Conv3Call& c, Conv3Params p, cudaStream_t st);
+int conv3c_cluster_size(int H, int W, int NB, int N);
+int conv3c_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
+                  Conv3Params p, bool a_mn, int cs, cudaStream_t st);
 
 // 512 x 512 fp16 identity: the weight of the "residual" K-segment of the persistent kernel.  y = conv(x) + r is run as
 // conv(x) + I * r on the tensor cores (exact: products by 1.0 accumulate in fp32), so the epilogue never has to gather
@@ -314,6 +317,14 @@ int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
     const char* m = getenv("BD_CONV3_EPI");
     p.epi_mode = m ? atoi(m) : 0;
   }
+  // cluster kernel (conv3c): 8 px x 32 row strips, weight tiles fetched in 128/cs-row slices and multicast
+  const int cs = (p.reg_n == 1 && !getenv("BD_NO_CONV3T") && !getenv("BD_NO_CONV3P")) ? conv3c_cluster_size(c.H, c.W, c.NB, c.N) : 0;
+  if (cs) {
+    p.reg_w = 8; p.pitch = 10; p.tiles_w = c.W / 8;
+    p.a_bytes = 10u * 34u * 128u;
+    p.a_sbo = (uint32_t)(p.pitch * 128) >> 4;
+  }
+  const uint32_t wrows = cs ? (uint32_t)(128 / cs) : 0;   // rows of one multicast slice
   CUtensorMap ma0, ma1, mb0, mb1;
   const uint32_t box[4] = {64, (uint32_t)p.reg_w + 2, (uint32_t)p.reg_h + 2, (uint32_t)p.reg_n};
   {
@@ -333,19 +344,20 @@ int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
     const int cols = c.b_mn ? c.N : c.Ca;
     uint64_t dims[3] = {(uint64_t)cols, (uint64_t)c.b_rows, 9};
     uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
-    uint32_t bbox[3] = {64, c.b_mn ? 64u : (uint32_t)C3_BN, 1};
+    uint32_t bbox[3] = {64, cs ? wrows : (c.b_mn ? 64u : (uint32_t)C3_BN), 1};
     if (!make_map(&mb0, c.b, 3, dims, str, bbox)) return BD_ERR_CUDA;
   }
   if (c.a2) {
     uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
     uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
-    uint32_t bbox[3] = {64, (uint32_t)C3_BN, 1};
+    uint32_t bbox[3] = {64, cs ? wrows : (uint32_t)C3_BN, 1};
     if (!make_map(&mb1, c.b2, 3, dims, str, bbox)) return BD_ERR_CUDA;
   } else {
     mb1 = mb0;
   }
   const int tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.reg_n);
   dim3 grid(tiles, c.N / C3_BN);
+  if (cs) return conv3c_launch(ma0, ma1, mb0, mb1, p, c.b_mn, cs, st);
   if (p.reg_n == 1 && !getenv("BD_NO_CONV3T"))  // H % 32 == 0: weights-as-A / 256-pixel-B orientation
     return conv3t_launch(ma0, ma1, mb0, mb1, p, c.b_mn, grid, st);
   static bool attr_set[2] = {false, false};
@@ -848,6 +860,372 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+
+// =============================================================================================================
+// Cluster variant of the persistent kernel ("conv3c", the default for H % 32 == 0): the epilogue of tile i runs UNDER
+// the MMAs of tile i+1.
+//   * Tile = 128 channels x 256 pixels (one 8 px x 32 row strip): ONE 256-column accumulator, so the 512 TMEM columns
+//     hold two tiles and the MMA warp ping-pongs between them while the 16 epilogue warps drain the other one.
+//   * A 256-pixel tile re-fetches every weight tile twice as often as the 512-pixel tile of umma_conv3p_kernel (41
+//     B/clk/SM of L2->SM traffic, the measured chip limit).  The CS CTAs of a thread-block cluster therefore walk CS
+//     neighbouring pixel tiles of the SAME channel slab in lockstep and share the weight ring: CTA r fetches rows
+//     [r*128/CS, (r+1)*128/CS) of each tap's 128 x 64 weight tile and TMA-MULTICASTS them into the ring slot of every
+//     CTA of the cluster; a slot is released by tcgen05.commit multicast to all CTAs' b_empty barriers (count CS), so
+//     no CTA overwrites a slot a peer's tensor core still reads.  L2->SM traffic per CTA: 43.5 KB halo + 147/CS KB of
+//     weights per 4.6 kcycles of MMA issue.
+//   * Everything else (orientation D[cout, pixel], taps as shifted descriptors of the resident halo tile, K-segments
+//     for the fused 1x1 shortcut / identity residual, stmatrix epilogue) is umma_conv3p_kernel's.
+// =============================================================================================================
+constexpr int C3C_A_STAGE_BYTES = 43 * 1024;          // >= 10*34*128 = 43,520
+constexpr int C3C_BSTAGES = 6;
+constexpr int C3C_B_OFFSET = C3_ASTAGES * C3C_A_STAGE_BYTES;
+constexpr int C3C_EPI_OFFSET = C3C_B_OFFSET + C3C_BSTAGES * C3_B_STAGE_BYTES;
+constexpr int C3C_BAR_OFFSET = C3C_EPI_OFFSET + C3P_EPI_BYTES;
+constexpr int C3C_SMEM = C3C_BAR_OFFSET + (2 * C3_ASTAGES + 2 * C3C_BSTAGES + 4) * 8 + 16 + 1024;
+static_assert(C3C_SMEM <= 232448, "conv3c shared memory");
+static_assert(C3C_A_STAGE_BYTES >= 10 * 34 * 128 && C3C_A_STAGE_BYTES % 1024 == 0, "conv3c halo stage");
+
+template <bool A_MN, int CS>
+__global__ void __launch_bounds__(576, 1) umma_conv3c_kernel(const __grid_constant__ CUtensorMap tmX0,
+                                                             const __grid_constant__ CUtensorMap tmX1,
+                                                             const __grid_constant__ CUtensorMap tmW0,
+                                                             const __grid_constant__ CUtensorMap tmW1,
+                                                             const Conv3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_w = smem + C3C_B_OFFSET;
+  uint8_t* smem_epi = smem + C3C_EPI_OFFSET;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + C3C_BAR_OFFSET);
+  uint64_t* a_empty = a_full + C3_ASTAGES;
+  uint64_t* b_full = a_empty + C3_ASTAGES;
+  uint64_t* b_empty = b_full + C3C_BSTAGES;
+  uint64_t* tmem_full = b_empty + C3C_BSTAGES;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int cluster_id = blockIdx.x / CS, nclusters = gridDim.x / CS;
+  const int per_n = p.tiles_w * p.tiles_h * p.NB;  // pixel tiles per 128-channel slab (a multiple of CS)
+  const int ngroups = per_n * (p.N / C3_BN) / CS;  // a group = CS neighbouring tiles of one slab, one per CTA
+  constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+  constexpr int kSliceRows = 128 / CS;             // weight-tile rows (K-major) / k rows of one 64-channel half (MN-major) per CTA
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmX0);
+    prefetch_tmap(&tmX1);
+    prefetch_tmap(&tmW0);
+    prefetch_tmap(&tmW1);
+    for (int s = 0; s < C3_ASTAGES; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+    for (int s = 0; s < C3C_BSTAGES; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], CS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 16); }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // every CTA's barriers exist before a peer multicasts into them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
+
+  if (warp == 0) {
+    // ===== TMA producer: halo tiles of this CTA (unicast) + this CTA's slice of every weight tile (multicast) =====
+    if (lane == 0) {
+      int as = 0, bs = 0;
+      uint32_t aph = 0, bph = 0;
+      bool ok = true;
+      for (int g = cluster_id; g < ngroups && ok; g += nclusters) {
+        const int tile = g * CS + rank;
+        const int n_tile = tile / per_n, rem = tile - n_tile * per_n;
+        const int tw = rem % p.tiles_w, th = (rem / p.tiles_w) % p.tiles_h, n0 = rem / (p.tiles_w * p.tiles_h);
+        const int w0 = tw * p.reg_w, h0 = th * p.reg_h;
+        for (int seg = 0; seg < 2 && ok; ++seg) {
+          const int nkb = seg ? p.nkb2 : p.nkb;
+          const int ntap = seg ? 1 : 9;
+          const CUtensorMap* mapX = seg ? &tmX1 : &tmX0;
+          const CUtensorMap* mapW = seg ? &tmW1 : &tmW0;
+          for (int kb = 0; kb < nkb && ok; ++kb) {
+            ok = mbar_wait(&a_empty[as], aph ^ 1, p.error_flag, 1);
+            if (!ok) break;
+            mbar_expect_tx(&a_full[as], p.a_bytes);
+            tma_load_4d(mapX, &a_full[as], smem + as * C3C_A_STAGE_BYTES, kb * C3_BK, w0 - 1, h0 - 1, n0);
+            for (int t = 0; t < ntap; ++t) {
+              ok = mbar_wait(&b_empty[bs], bph ^ 1, p.error_flag, 1);   // released by ALL CTAs of the cluster
+              if (!ok) break;
+              uint8_t* sw = smem_w + bs * C3_B_STAGE_BYTES;
+              mbar_expect_tx(&b_full[bs], C3_B_STAGE_BYTES);            // the CS slices that land in THIS CTA's slot
+              if (!A_MN) {
+                tma_load_3d_mc(mapW, &b_full[bs], sw + rank * kSliceRows * 128, kb * C3_BK, n_tile * C3_BN + rank * kSliceRows, t, kMask);
+              } else {
+                // MN-major tile = two [64 k][64 n] halves; CTA r owns k rows [part*kSliceRows, +kSliceRows) of half `half`
+                const int half = rank / (CS / 2), part = rank % (CS / 2);
+                tma_load_3d_mc(mapW, &b_full[bs], sw + half * (64 * C3_BK * 2) + part * kSliceRows * 128,
+                               n_tile * C3_BN + half * 64, kb * C3_BK + part * kSliceRows, t, kMask);
+              }
+              if (++bs == C3C_BSTAGES) { bs = 0; bph ^= 1; }
+            }
+            if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: accumulator (tile & 1) =====
+    if (lane == 0) {
+      int as = 0, bs = 0, acc = 0, di = 0;
+      uint32_t aph = 0, bph = 0, tph = 0;   // tph: bit `acc` = phase of accumulator acc
+      bool ok = true;
+      for (int g = cluster_id; g < ngroups && ok; g += nclusters) {
+        ok = mbar_wait(&tmem_empty[acc], ((tph >> acc) & 1u) ^ 1u, p.error_flag, 4);  // drained by the epilogue two tiles ago
+        if (!ok) break;
+        tc_fence_after();
+        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di] = clock64();   // [4i]: tile i may start
+        const uint32_t tacc = tmem_base + acc * 256;
+        bool first = true;
+        for (int seg = 0; seg < 2 && ok; ++seg) {
+          const int nkb = seg ? p.nkb2 : p.nkb;
+          const int ntap = seg ? 1 : 9;
+          for (int kb = 0; kb < nkb && ok; ++kb) {
+            ok = mbar_wait(&a_full[as], aph, p.error_flag, 2);
+            if (!ok) break;
+            const uint32_t sx = smem_u32(smem + as * C3C_A_STAGE_BYTES);
+            for (int t = 0; t < ntap; ++t) {
+              ok = mbar_wait(&b_full[bs], bph, p.error_flag, 2);
+              if (!ok) break;
+              tc_fence_after();
+              int dy = seg ? 0 : t / 3 - 1, dx = seg ? 0 : t % 3 - 1;
+              if (p.flip) { dy = -dy; dx = -dx; }
+              const uint32_t sw = smem_u32(smem_w + bs * C3_B_STAGE_BYTES);
+              const uint32_t x0 = sx + (uint32_t)((dy + 1) * p.pitch + (dx + 1)) * 128u;
+#pragma unroll
+              for (int k = 0; k < C3_BK / 16; ++k) {
+                const uint64_t wd = A_MN ? make_desc(sw + k * 2048, 512, 64) : make_desc(sw + k * 32, 1, 64);
+                const uint64_t xd = make_desc(x0 + k * 32, 1, p.a_sbo);
+                umma_f16(tacc, wd, xd, p.idesc, (first && k == 0) ? 0u : 1u);
+              }
+              first = false;
+              umma_commit_mc(&b_empty[bs], kMask);   // this CTA is done with the slot: tell every producer of the cluster
+              if (++bs == C3C_BSTAGES) { bs = 0; bph ^= 1; }
+            }
+            if (ok) umma_commit(&a_empty[as]);
+            if (++as == C3_ASTAGES) { as = 0; aph ^= 1; }
+          }
+        }
+        if (ok) umma_commit(&tmem_full[acc]);
+        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di + 1] = clock64();  // [4i+1]: last MMA of tile i issued
+        di += 4;
+        tph ^= 1u << acc;
+        acc ^= 1;
+      }
+    }
+  } else {
+    // ===== epilogue: 16 warps; warp quadrant q owns channels 32q..32q+31 (TMEM lanes), group g4 the 64 pixel columns
+    // [64 g4, 64 g4 + 64) = image rows 8 g4 .. 8 g4 + 7 of the strip =====
+    const int q = warp & 3, g4 = (warp - 2) >> 2;
+    const int ch = q * 32 + lane;
+    uint32_t tph = 0;
+    int acc = 0, di = 0;
+    bool ok = true;
+    for (int g = cluster_id; g < ngroups && ok; g += nclusters) {
+      const bool stamp = p.dbg && warp == 2 && lane == 0 && di < 60;
+      const int tile = g * CS + rank;
+      const int n_tile = tile / per_n, rem = tile - n_tile * per_n;
+      const int tw = rem % p.tiles_w, th = (rem / p.tiles_w) % p.tiles_h, n0 = rem / (p.tiles_w * p.tiles_h);
+      const int w0 = tw * p.reg_w, h0 = th * p.reg_h;
+      const int gcol = n_tile * C3_BN + ch;
+      float badd = 0.f;
+      if (p.bias) badd += p.bias[gcol];
+      if (p.bias2) badd += p.bias2[gcol];
+      if (p.rowbias) badd += p.rowbias[(int64_t)n0 * p.ld_rowbias + gcol];
+      float bq[4];
+      {
+        const int fr = lane >> 2;                 // fragment row: channels fr, fr+8 (+16, +24 for the upper half-quadrant)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int c = n_tile * C3_BN + q * 32 + fr + 8 * i;
+          float b = 0.f;
+          if (p.bias) b += p.bias[c];
+          if (p.bias2) b += p.bias2[c];
+          if (p.rowbias) b += p.rowbias[(int64_t)n0 * p.ld_rowbias + c];
+          bq[i] = b;
+        }
+      }
+      ok = mbar_wait(&tmem_full[acc], (tph >> acc) & 1u, p.error_flag, 3);
+      tph ^= 1u << acc;
+      if (!ok) break;
+      tc_fence_after();
+      if (stamp) p.dbg[(size_t)blockIdx.x * 64 + di + 2] = clock64();   // [4i+2]: accumulator of tile i complete
+      const uint32_t tacc = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
+      if (!p.out_f32 && !p.residual) {
+        // fp16 output: TMEM fragments -> f16x2 -> stmatrix.trans into a warp-private [16 px][32 ch] tile -> 16-byte
+        // read-back -> st.global.v4 (every warp store = 8 pixels x 64 contiguous bytes)
+        const uint32_t stage = smem_u32(smem_epi + (warp - 2) * 16 * C3P_EPI_PITCH);
+        const uint32_t st_addr = stage + (uint32_t)(((lane & 7) + ((lane >> 4) & 1) * 8) * C3P_EPI_PITCH + ((lane >> 3) & 1) * 16);
+        const uint32_t rd_addr = stage + (uint32_t)((lane >> 2) * C3P_EPI_PITCH + (lane & 3) * 16);
+        const float sc = p.scale;
+        __half* ybase = reinterpret_cast<__half*>(p.y) + n_tile * C3_BN + q * 32 + (lane & 3) * 8;
+        uint32_t va[8], vb[8];
+        tmem_ld_16x256b_x2_nowait(tacc + g4 * 64, va);
+        tmem_ld_16x256b_x2_nowait(tacc + (16u << 16) + g4 * 64, vb);
+#pragma unroll 1
+        for (int j0 = g4 * 64; j0 < g4 * 64 + 64; j0 += 16) {
+          tmem_wait_ld();
+          uint32_t m[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            m[i] = pack_f16x2((__uint_as_float(va[2 * i]) + bq[i & 1]) * sc, (__uint_as_float(va[2 * i + 1]) + bq[i & 1]) * sc);
+            m[4 + i] = pack_f16x2((__uint_as_float(vb[2 * i]) + bq[2 + (i & 1)]) * sc, (__uint_as_float(vb[2 * i + 1]) + bq[2 + (i & 1)]) * sc);
+          }
+          if (j0 + 16 < g4 * 64 + 64) {
+            tmem_ld_16x256b_x2_nowait(tacc + j0 + 16, va);
+            tmem_ld_16x256b_x2_nowait(tacc + (16u << 16) + j0 + 16, vb);
+          }
+          __syncwarp();   // the previous chunk's read-back is complete
+          stmatrix_x4_trans(st_addr, m[0], m[1], m[2], m[3]);
+          stmatrix_x4_trans(st_addr + 32, m[4], m[5], m[6], m[7]);
+          __syncwarp();
+          // chunk = image rows (j0>>3), (j0>>3)+1 of the strip, 8 pixels each; this lane: pixel (lane>>2) of each row
+          const int64_t m0 = ((int64_t)n0 * p.H + h0 + (j0 >> 3)) * p.W + w0 + (lane >> 2);
+#pragma unroll
+          for (int it = 0; it < 2; ++it) {
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(rd_addr + it * 8 * C3P_EPI_PITCH));
+            *reinterpret_cast<uint4*>(ybase + (m0 + (int64_t)it * p.W) * p.ld_y) = val;
+          }
+        }
+      } else {
+        const int ldr = (int)p.ld_res, ldy = (int)p.ld_y;
+#pragma unroll 1
+        for (int j0 = g4 * 64; j0 < g4 * 64 + 64; j0 += 16) {
+          uint32_t v[16];
+          tmem_ld16_nowait(tacc + j0, v);
+          const int64_t m0 = ((int64_t)n0 * p.H + h0 + (j0 >> 3)) * p.W + w0;
+          unsigned short res[16];
+          if (p.residual) {
+            const unsigned short* rp = reinterpret_cast<const unsigned short*>(p.residual) + m0 * p.ld_res + gcol;
+#pragma unroll
+            for (int r = 0; r < 2; ++r) {
+              const unsigned short* rr = rp + (int64_t)r * p.W * p.ld_res;
+#pragma unroll
+              for (int px = 0; px < 8; ++px) res[r * 8 + px] = rr[px * ldr];
+            }
+          }
+          tmem_wait_ld();
+#pragma unroll
+          for (int r = 0; r < 2; ++r) {
+#pragma unroll
+            for (int px = 0; px < 8; ++px) {
+              float f = __uint_as_float(v[r * 8 + px]) + badd;
+              if (p.residual) f += __half2float(__ushort_as_half(res[r * 8 + px]));
+              f *= p.scale;
+              const int64_t off = (m0 + (int64_t)r * p.W + px) * ldy + gcol;
+              if (p.out_f32) reinterpret_cast<float*>(p.y)[off] = f;
+              else reinterpret_cast<__half*>(p.y)[off] = __float2half_rn(f);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (stamp) p.dbg[(size_t)blockIdx.x * 64 + di + 3] = clock64();   // [4i+3]: this warp's share of tile i stored
+      di += 4;
+      acc ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();   // no CTA retires while a peer may still multicast into its ring or arrive on its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, int cs,
+                                             cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cs;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = getenv("BD_NO_PDL") ? 1 : 2;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// cluster size of the conv3c kernel for this launch (0: use the non-cluster persistent kernel).
+// Measured on B200 (scripts/ab_conv3c.py): a 256-pixel tile makes shared memory the bound -- 96 B/clk of MMA operand reads
+// + 41 B/clk of TMA fills + the overlapped epilogue's stmatrix / read-back against the 128 B/clk port: 13.9 kcycles of MMA
+// issue per 256-pixel tile (ideal 9.2 k) against 19.4 k per 512-pixel tile for conv3p -- so hiding the epilogue buys
+// nothing at 128 -> 128 @ 32x32, B = 128 (38.0 vs 39.5 us).  What the smaller tile does buy is a finer walk: the cluster
+// kernel wins whenever 512-pixel tiles fill the last round over the SMs badly and 256-pixel tiles fill it better
+// (CelebA-HQ shapes: 4 x 256x256 128->128 -9 %, 4 x 64x64 256->256 -30 %; 256->256 @ 32x32 B = 128 -3 %).  Cluster size 4
+// never beat 2 (weights are not the binding traffic once multicast halves them).
+// BD_CONV3C=0 disables, BD_CONV3C=2|4 forces that cluster size, unset = the round-fill heuristic with clusters of 2.
+int conv3c_cluster_size(int H, int W, int NB, int N) {
+  const char* e = getenv("BD_CONV3C");
+  const int forced = e ? atoi(e) : -1;
+  if (forced == 0) return 0;
+  if (H % 32 || W % 8) return 0;
+  const long long per_n = (long long)(W / 8) * (H / 32) * NB;
+  if (forced == 2 || forced == 4) return per_n % forced == 0 ? forced : 0;
+  if (per_n % 2 || W % 16) return 0;
+  const long long sms = num_sms(), slabs = N / C3_BN;
+  const long long n256 = per_n * slabs, n512 = n256 / 2;
+  const double fill512 = (double)n512 / (double)(((n512 + sms - 1) / sms) * sms);
+  const long long cl = sms / 2, g256 = n256 / 2;   // groups of 2 tiles walk over sms/2 clusters
+  const double fill256 = (double)g256 / (double)(((g256 + cl - 1) / cl) * cl);
+  return fill256 > fill512 + 0.05 ? 2 : 0;
+}
+
+int conv3c_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
+                  Conv3Params p, bool a_mn, int cs, cudaStream_t st) {
+  p.idesc = (1u << 4) | ((a_mn ? 1u : 0u) << 15) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int ngroups = p.tiles_w * p.tiles_h * p.NB * (p.N / C3_BN) / cs;
+  int nclusters = num_sms() / cs;
+  if (nclusters > ngroups) nclusters = ngroups;
+  void (*k)(CUtensorMap, CUtensorMap, CUtensorMap, CUtensorMap, Conv3Params) =
+      cs == 4 ? (a_mn ? umma_conv3c_kernel<true, 4> : umma_conv3c_kernel<false, 4>)
+              : (a_mn ? umma_conv3c_kernel<true, 2> : umma_conv3c_kernel<false, 2>);
+  // The tile walk is static (group g -> cluster g % nclusters): every cluster must be resident at once.  A GPC whose SM
+  // count is not a multiple of cs cannot host a cluster on its last SMs, so ask the driver how many fit.
+  static int max_clusters[4] = {0, 0, 0, 0};
+  const int ai = (cs == 4 ? 2 : 0) + (a_mn ? 1 : 0);
+  if (!max_clusters[ai]) {
+    cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C3C_SMEM);
+    cudaLaunchConfig_t q = {};
+    q.gridDim = dim3((num_sms() / cs) * cs);
+    q.blockDim = dim3(576);
+    q.dynamicSmemBytes = C3C_SMEM;
+    cudaLaunchAttribute qa[1];
+    qa[0].id = cudaLaunchAttributeClusterDimension;
+    qa[0].val.clusterDim.x = cs; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+    q.attrs = qa; q.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, k, &q) != cudaSuccess || n < 1) { cudaGetLastError(); n = num_sms() / cs; }
+    max_clusters[ai] = (int)env_u32("BD_CONV3C_CLUSTERS", (uint32_t)n);
+  }
+  if (nclusters > max_clusters[ai]) nclusters = max_clusters[ai];
+  cudaError_t e = launch_pdl_cluster(k, dim3(nclusters * cs), dim3(576), C3C_SMEM, cs, st, mx0, mx1, mw0, mw1, p);
+  if (e != cudaSuccess) { set_error("conv3c: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+  count_launch(1);
+  return BD_OK;
 }
 
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,

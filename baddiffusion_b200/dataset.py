@@ -198,3 +198,41 @@ class SyntheticDataset:
         if pin and torch.cuda.is_available():
             img, isp = img.pin_memory(), isp.pin_memory()
         return PoisonedBatch(img, isp)
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU data path: the host hands over DECODED pixels and coins, the device does the rest
+# ------------------------------------------------------------------------------------------------
+def draw_flips(n: int, generator: Optional[torch.Generator] = None, p: float = 0.5) -> torch.Tensor:
+    """The coins of the reference's `transforms.RandomHorizontalFlip()` (dataset.py:126-128): one `torch.rand(1) < p`
+    per image in batch order (generator None = the global generator, exactly the stream torchvision consumes)."""
+    return torch.tensor([bool(torch.rand(1, generator=generator) < p) for _ in range(n)], dtype=torch.uint8)
+
+
+@dataclass
+class PoisonedBatchU8:
+    """Decoded uint8 NHWC pixels + h-flip coins + poison flags: what `Trainer.step_u8` consumes.  ToTensor, normalize
+    (Q7), the flip, the mask/blend and add_noise all run inside `bd_batch_prep_u8` (4x fewer H2D bytes than fp32 NCHW,
+    none of the reference's 8 PIL/torchvision worker processes past the decode)."""
+    image_u8: torch.Tensor    # (B,H,W,C) uint8
+    flip: torch.Tensor        # (B,) uint8
+    is_poison: torch.Tensor   # (B,) uint8
+
+
+def u8_batch_to_image(image_u8: torch.Tensor, flip: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Device-side equivalent of the reference's per-image transform chain for already-sized RGB images (dataset.py:
+    120-136): (B,H,W,C) uint8 on the GPU -> (B,C,H,W) fp32 in [-1, 1-2e-5], bit-exact (`bd_batch_prep_u8`'s image_out)."""
+    from . import ops
+    from .schedulers import DDPMScheduler
+
+    if image_u8.device.type != "cuda":
+        raise RuntimeError("u8_batch_to_image runs on the GPU (no CPU path): move the uint8 batch to the device")
+    B, H, W, C = image_u8.shape
+    dev = image_u8.device
+    sched = DDPMScheduler()
+    sched._to_device(dev)
+    out = torch.empty(B, C, H, W, device=dev)
+    t = torch.zeros(B, dtype=torch.int64, device=dev)
+    ops.batch_prep_u8(image_u8.contiguous(), None if flip is None else flip.to(dev, torch.uint8), None, None, None, t,
+                      sched._alphas_dev, sched._acp_dev, noise=torch.zeros(B, C, H, W, device=dev), image_out=out)
+    return out

@@ -46,7 +46,7 @@ class Trainer:
                  target: torch.Tensor, lr: float = 2e-4, total_steps: int = 23450, warmup_steps: int = 500,
                  max_grad_norm: float = 1.0, betas=(0.9, 0.999), eps: float = 1e-8, init_scale: float = 65536.0,
                  growth_interval: int = 2000, use_graph: Optional[bool] = None, process_group=None, seed: int = 0,
-                 lr_table_len: int = 0, accum_steps: int = 1):
+                 lr_table_len: int = 0, accum_steps: int = 1, u8_input: bool = False):
         if not model.device.type == "cuda":
             raise RuntimeError("Trainer needs the model on a CUDA device")
         self.model, self.sched, self.B = model, noise_sched, batch
@@ -67,6 +67,11 @@ class Trainer:
         # static device buffers (graph inputs / outputs)
         self.img = torch.zeros(self.shape, device=dev)
         self.isp = torch.zeros(batch, dtype=torch.uint8, device=dev)
+        # u8_input: the batch is fed as decoded uint8 NHWC pixels + per-sample h-flip coins (load_batch_u8 / step_u8);
+        # the choice is baked into the captured graph like the noise mode
+        self.u8_input = bool(u8_input)
+        self.img_u8 = torch.zeros((batch, S, S, C), dtype=torch.uint8, device=dev) if u8_input else None
+        self.flip = torch.zeros(batch, dtype=torch.uint8, device=dev) if u8_input else None
         self.t = torch.zeros(batch, dtype=torch.int64, device=dev)
         self.noise = torch.zeros(self.shape, device=dev)
         self.x_noisy = torch.empty(self.shape, device=dev)
@@ -121,9 +126,14 @@ class Trainer:
         eng._fork(lambda: ops.cast_f32_to_f16(self.flat[: self.model.layout.n_gemm], eng.flat16))
         if zero:
             eng._fork(self.gflat.zero_)
-        ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
-                       noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
-                       x_noisy=self.x_noisy, eps_target=self.eps_target, noise_out=None, noise_counter=self.iter_dev)
+        if self.u8_input:   # decoded uint8 NHWC pixels in, ToTensor / normalize / h-flip fused into batch-prep
+            ops.batch_prep_u8(self.img_u8, self.flip, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
+                              noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
+                              x_noisy=self.x_noisy, eps_target=self.eps_target, noise_counter=self.iter_dev)
+        else:
+            ops.batch_prep(self.img, self.isp, self.trigger, self.target, self.t, self.alphas, self.acp,
+                           noise=None if philox_noise else self.noise, seed=self.seed, offset=0,
+                           x_noisy=self.x_noisy, eps_target=self.eps_target, noise_out=None, noise_counter=self.iter_dev)
         self.iter_dev.add_(1)
         eng.io["x"], eng.io["t"], eng.io["d_eps"] = self.x_noisy, self.t, self.d_eps
         eng.run_forward()
@@ -188,7 +198,30 @@ class Trainer:
     def step(self, image: torch.Tensor, is_poison: torch.Tensor, noise: Optional[torch.Tensor] = None,
              t: Optional[torch.Tensor] = None) -> torch.Tensor:
         """One optimisation step on one (local) batch; returns the device loss tensor (no host sync)."""
+        if self.u8_input:
+            raise RuntimeError("this Trainer was built with u8_input=True: feed it with step_u8()")
         self.load_batch(image, is_poison, noise, t)
+        return self.step_resident(philox_noise=noise is None)
+
+    def load_batch_u8(self, image_u8: torch.Tensor, flip: torch.Tensor, is_poison: torch.Tensor,
+                      noise: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None):
+        """Decoded pixels (B, S, S, C) uint8 NHWC + h-flip coins (dataset.draw_flips) -> the static device buffers:
+        a quarter of the fp32 batch's H2D bytes, and no CPU-side ToTensor / normalize / flip (dataset.py:120-136)."""
+        if not self.u8_input:
+            raise RuntimeError("build the Trainer with u8_input=True to feed uint8 batches")
+        self.img_u8.copy_(image_u8, non_blocking=True)
+        self.flip.copy_(flip.to(torch.uint8), non_blocking=True)
+        self.isp.copy_(is_poison.to(torch.uint8), non_blocking=True)
+        if t is None:
+            self.t.copy_(torch.randint(0, self.T, (self.B,), device=self.dev))
+        else:
+            self.t.copy_(t, non_blocking=True)
+        if noise is not None:
+            self.noise.copy_(noise, non_blocking=True)
+
+    def step_u8(self, image_u8: torch.Tensor, flip: torch.Tensor, is_poison: torch.Tensor,
+                noise: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None) -> torch.Tensor:
+        self.load_batch_u8(image_u8, flip, is_poison, noise, t)
         return self.step_resident(philox_noise=noise is None)
 
     def step_resident(self, philox_noise: bool = True) -> torch.Tensor:

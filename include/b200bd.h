@@ -59,6 +59,17 @@ int bd_batch_prep(const float* img, const uint8_t* is_poison, const float* trigg
                   const int* noise_counter /* device int added to `offset` (nullable): new noise per graph replay */,
                   void* stream);
 
+/* K11 with the data path of SURVEY 8f n2 folded in: the batch arrives as decoded uint8 NHWC pixels (B,H,W,C);
+ * transforms.ToTensor (/255), util.normalize (util.py:83-111 with vmin_in 0, vmax_in 1 -> [-1, 1-2e-5], quirk Q7) and
+ * RandomHorizontalFlip (dataset.py:120-136; the per-sample coin `flip` (B) u8 is drawn by the host, nullable = never)
+ * run on load, then the poison blend / add_noise / loss target of bd_batch_prep.  Bit-exact with the reference's
+ * CPU transform chain.  image_out (B,C,H,W) f32 nullable: the normalised, flipped image (the DataLoader's `image`). */
+int bd_batch_prep_u8(const uint8_t* img_nhwc, const uint8_t* flip, const uint8_t* is_poison, const float* trigger,
+                     const float* target, const float* noise, const int64_t* t, const float* alphas,
+                     const float* alphas_cumprod, float* x_noisy, float* eps_target, float* noise_out, float* image_out,
+                     int B, int C, int H, int W, int T, uint64_t seed, uint64_t offset, const int* noise_counter,
+                     void* stream);
+
 /* K12  loss.py:301 F.mse_loss(target, eps_hat) and its gradient 2(eps_hat-target)/n * loss_scale.
  *   partial: workspace of >= bd_mse_workspace_floats() floats; loss: 1 float; grad nullable (f32, same
  *   layout as eps_hat); loss_scale: device pointer to 1 float (nullable -> 1). Deterministic 2-stage sum. */

@@ -409,6 +409,20 @@ def normalize(x, vmin_in=0.0, vmax_in=1.0, vmin_out=-1.0, vmax_out=1.0, eps=1e-5
     return ((x - vmin_in) / (vmax_in - vmin_in + eps)) * (vmax_out - vmin_out) + vmin_out
 
 
+def u8_batch_to_image(u8_nhwc, flips) -> torch.Tensor:
+    """dataset.py:120-136 on an already-sized RGB batch: ToTensor (uint8 HWC -> fp32 CHW / 255), util.normalize to
+    [-1, 1 - 2e-5] (quirk Q7), RandomHorizontalFlip with the per-sample coins `flips` (drawn by draw_flips)."""
+    x = torch.as_tensor(u8_nhwc).permute(0, 3, 1, 2).to(torch.float32).div(255)
+    x = normalize(x)
+    fl = torch.as_tensor(flips, dtype=torch.bool).view(-1, 1, 1, 1)
+    return torch.where(fl, x.flip(-1), x)
+
+
+def draw_flips(n: int, generator=None, p: float = 0.5) -> torch.Tensor:
+    """torchvision RandomHorizontalFlip.forward: one `torch.rand(1) < p` per image, in batch order."""
+    return torch.tensor([bool(torch.rand(1, generator=generator) < p) for _ in range(n)])
+
+
 def _load_bitmap(path: str, size, channel: int = 3) -> torch.Tensor:
     """dataset.py:420-434: convert -> Resize(bilinear, antialias) -> ToTensor -> normalize."""
     from PIL import Image

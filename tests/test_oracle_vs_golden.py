@@ -240,3 +240,21 @@ def test_cosine_lr(golden):
     lrs = golden("cosine_lr")["lrs"]
     mine = np.array([2e-4 * O.cosine_lr_lambda(i, 500, 2000) for i in range(2000)])
     assert np.abs(mine - lrs).max() < 1e-12
+
+
+def test_u8_data_path_matches_reference_transforms(golden):
+    """oracle restatement of ToTensor + normalize + RandomHorizontalFlip + mask/blend vs the reference
+    DatasetLoader's own transform closures (fixture: scripts/make_goldens_r2.py)."""
+    g = golden("data_path")
+    for tag in ("cifar", "celeba"):
+        u8, flips = g[f"{tag}/u8"], g[f"{tag}/flips"]
+        coins = O.draw_flips(len(u8), generator=torch.Generator().manual_seed(int(g[f"{tag}/seed"])))
+        assert np.array_equal(coins.numpy(), flips)     # global-generator stream == explicit generator with that seed
+        img = O.u8_batch_to_image(u8, flips)
+        assert np.array_equal(img.numpy(), g[f"{tag}/clean/image"]) and np.array_equal(img.numpy(), g[f"{tag}/backdoor/image"])
+        trig, targ = torch.from_numpy(g[f"{tag}/trigger"]), torch.from_numpy(g[f"{tag}/target_tensor"])
+        B = len(u8)
+        R, x0 = O.poison_blend(img, torch.ones(B, dtype=torch.bool), trig, targ)
+        assert np.array_equal(R.numpy(), g[f"{tag}/backdoor/pixel_values"]) and np.array_equal(x0.numpy(), g[f"{tag}/backdoor/target"])
+        R, x0 = O.poison_blend(img, torch.zeros(B, dtype=torch.bool), trig, targ)
+        assert np.array_equal(R.numpy(), g[f"{tag}/clean/pixel_values"]) and np.array_equal(x0.numpy(), g[f"{tag}/clean/target"])

@@ -200,3 +200,41 @@ def test_two_rank_nccl_gradient_matches_global_batch(tmp_path):
         assert v[mode]["grad_cos"] >= 0.9999 and v[mode]["grad_norm_rel"] <= 2e-3, v
         assert v[mode]["loss_rel"] <= 1e-4 and v[mode]["replicas_equal"], v
         assert v[mode]["param_max_abs"] <= 1e-4, v
+
+
+def test_trainer_u8_input_equals_fp32_input():
+    """SURVEY 8f n2 end to end: Trainer(u8_input=True).step_u8(decoded pixels, coins) == Trainer.step(the fp32 NCHW batch
+    the reference's DataLoader would have produced from the same pixels) -- bitwise equal loss (same x_noisy / target)."""
+    from baddiffusion_b200.dataset import Backdoor, draw_flips
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from baddiffusion_b200.train import Trainer
+    from baddiffusion_b200.unet import UNet2DModel
+    from oracle import torch_ref as O
+
+    cfg = dict(O.TINY_CONFIG, block_out_channels=(64, 128))
+    sd0 = O.make_state_dict(cfg, 2)
+    S, B = 32, 8
+    bd = Backdoor(root="datasets")
+    trig = bd.get_trigger(type="BOX_14", channel=3, image_size=S)
+    targ = bd.get_target(type="HAT", trigger=trig)
+    g = torch.Generator().manual_seed(11)
+    u8 = torch.randint(0, 256, (B, S, S, 3), generator=g, dtype=torch.uint8)
+    coins = draw_flips(B, generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    noise = torch.randn(B, 3, S, S, generator=g)
+    isp = torch.tensor([i % 3 == 0 for i in range(B)])
+    image = O.u8_batch_to_image(u8, coins.bool())       # oracle = the reference's transform chain (pinned on CPU)
+    losses = {}
+    for mode in ("fp32", "u8"):
+        m = UNet2DModel(**cfg)
+        m.load_state_dict(sd0)
+        m = m.cuda()
+        tr = Trainer(m, DDPMScheduler(variance_type="fixed_large"), B, trig, targ, lr=1e-3, total_steps=10, warmup_steps=0,
+                     u8_input=(mode == "u8"))
+        if mode == "u8":
+            with pytest.raises(RuntimeError):
+                tr.step(image, isp, noise=noise, t=t)
+            losses[mode] = float(tr.step_u8(u8, coins, isp, noise=noise, t=t))
+        else:
+            losses[mode] = float(tr.step(image, isp, noise=noise, t=t))
+    assert losses["u8"] == losses["fp32"], losses
