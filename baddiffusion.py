@@ -27,8 +27,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from baddiffusion_b200.dataset import Backdoor, PoisonedBatch, SyntheticDataset, normalize  # noqa: E402
-from baddiffusion_b200.model import (DiffuserModelSched, batch_sampling, batch_sampling_save, save_imgs,  # noqa: E402
-                                     shard_for_rank)
+from baddiffusion_b200.model import (DiffuserModelSched, backdoor_metrics, batch_sampling, batch_sampling_save,  # noqa: E402
+                                     batch_sampling_u8, save_imgs, save_imgs_u8, shard_for_rank)
 
 MODE_TRAIN, MODE_RESUME, MODE_SAMPLING, MODE_MEASURE, MODE_TRAIN_MEASURE = "train", "resume", "sampling", "measure", "train+measure"
 DATASETS = {"MNIST": (28, 1), "CIFAR10": (32, 3), "CELEBA": (64, 3), "CELEBA-HQ": (256, 3)}
@@ -262,8 +262,8 @@ def sampling(config, file_name, pipeline, data):
 
 
 def measure(config, pipeline, data, rank, world):
-    """baddiffusion.py:477-551 minus FID (pytorch-fid unavailable offline): MSE of the backdoor samples to the
-    target; samples are sharded across ranks with no collective."""
+    """baddiffusion.py:477-551 minus FID (pytorch-fid unavailable offline): MSE and SSIM of the backdoor samples to the
+    target; samples are sharded across ranks, the only collective is the sum of three scalars in backdoor_metrics."""
     S, C, N = data.size, data.channel, int(os.environ.get("BD_MEASURE_N", config.measure_sample_n))
     tag = "_noclip" if config.fclip != "w" else ""
     root = os.path.join(config.output_dir, "measure" if config.sample_ep is None else f"measure/ep{config.sample_ep}")
@@ -272,18 +272,14 @@ def measure(config, pipeline, data, rank, world):
     rng = torch.Generator().manual_seed(config.seed + rank)
     batch_sampling_save(hi - lo, pipeline, os.path.join(root, f"clean{tag}"), init=noise[lo:hi],
                         max_batch_n=config.eval_max_batch, rng=rng, start_cnt=lo)
-    bd_imgs = batch_sampling(hi - lo, pipeline, init=noise[lo:hi] + data.trigger[None], max_batch_n=config.eval_max_batch, rng=rng)
-    save_imgs(bd_imgs, os.path.join(root, f"backdoor{tag}"), start_cnt=lo)
-    tgt = ((data.target / 2 + 0.5).clamp(0, 1)).permute(1, 2, 0).numpy()[None]
-    se = float(((bd_imgs - tgt) ** 2).mean()) * (hi - lo)
-    if world > 1:
-        t = torch.tensor([se, float(hi - lo)], device="cuda")
-        torch.distributed.all_reduce(t)
-        se, cnt = float(t[0]), float(t[1])
-    else:
-        cnt = float(hi - lo)
-    score = {"FID": None, "MSE": se / max(cnt, 1.0), "SSIM": None,
-             "note": "FID/SSIM need pytorch-fid / torchmetrics (unavailable offline); MSE is backdoor-sample vs target"}
+    # backdoor samples stay on the GPU as the uint8 pixels of the PNG files; MSE and SSIM come from one device kernel
+    # (no save -> ImagePathDataset re-read as in baddiffusion.py:539), the files are still written for the user
+    bd_u8 = batch_sampling_u8(hi - lo, pipeline, init=noise[lo:hi] + data.trigger[None], max_batch_n=config.eval_max_batch, rng=rng)
+    save_imgs_u8(bd_u8, os.path.join(root, f"backdoor{tag}"), start_cnt=lo)
+    mse_sc, ssim_sc = backdoor_metrics(bd_u8, data.target)
+    score = {"FID": None, "MSE": mse_sc, "SSIM": ssim_sc,
+             "note": "FID needs pytorch-fid + Inception weights (unavailable offline); MSE / SSIM: backdoor samples vs target, "
+                     "computed on the device from the uint8 pixels of the saved PNGs (torchmetrics SSIM defaults)"}
     if rank == 0:
         with open(os.path.join(config.output_dir, "score.json"), "w") as f:
             json.dump(score, f, indent=4)

@@ -51,6 +51,7 @@ _SIGS = {
     "bd_ddim_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),
     "bd_sampler_advance": (i32, [vp, vp, vp, i32, i32, vp]),
     "bd_finalize_images": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
+    "bd_image_metrics": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "bd_temb_mlp": (i32, [vp] * 9 + [i32, i32, i32, i32, vp, vp]),
     "bd_sgemm": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_gn_workspace_floats": (sz, [i32, i32]),

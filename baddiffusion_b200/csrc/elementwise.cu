@@ -403,6 +403,88 @@ __global__ void scaler_update_kernel(float* state, int* step, float growth, floa
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Measurement tail on the device (baddiffusion.py:533-546): MSE and SSIM of the generated uint8 samples
+// against the backdoor target WITHOUT the PNG write / re-read of the reference (save_imgs -> ImagePathDataset).
+//   x = u8 / 255 (transforms.ToTensor on the saved PNG), y = (target / 2 + 0.5).clamp(0, 1) (baddiffusion.py:542)
+//   MSE  = mean (x - y)^2                                        (nn.MSELoss, :545)
+//   SSIM = torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0) defaults: 11x11 Gaussian window, sigma 1.5,
+//          k1 0.01, k2 0.03, reflect padding that the final crop removes again -> the mean of the SSIM map over the
+//          window centres whose 11x11 support lies inside the image ((H-10) x (W-10) per channel).
+// One CTA = one 32x32 block of centres of one (image, channel): the 42x42 supports of x and y sit in shared memory, the
+// five Gaussian-filtered maps (x, y, xx, yy, xy) are formed separably (row pass into shared memory, column pass in
+// registers).  acc[0] += sum of squared errors, acc[1] += sum of SSIM values (fp64 atomics; the host divides).
+// Algorithmic bytes / element: 1 (u8) + 4 (target, L2-resident) -- HBM traffic is the 1 B/elt sample read.
+// ---------------------------------------------------------------------------------------------
+constexpr int SS_T = 32, SS_R = 5, SS_P = SS_T + 2 * SS_R;   // tile, window radius, padded tile
+struct SsimWindow { float g[2 * SS_R + 1]; };
+__global__ void __launch_bounds__(256) image_metrics_kernel(const uint8_t* __restrict__ img, const float* __restrict__ target,
+                                                            double* __restrict__ acc, int C, int H, int W, int tiles_x,
+                                                            SsimWindow win) {
+  __shared__ float sx[SS_P][SS_P + 1], sy[SS_P][SS_P + 1];
+  __shared__ float hq[5][SS_P][SS_T + 1];
+  __shared__ double red[2][8];
+  const int tx = blockIdx.x % tiles_x, ty = blockIdx.x / tiles_x, ch = blockIdx.y, b = blockIdx.z;
+  const int y0 = ty * SS_T - SS_R, x0 = tx * SS_T - SS_R;
+  double se = 0.0;
+  for (int i = threadIdx.x; i < SS_P * SS_P; i += blockDim.x) {
+    const int r = i / SS_P, c = i % SS_P, gy = y0 + r, gx = x0 + c;
+    float xv = 0.f, yv = 0.f;
+    if (gy >= 0 && gy < H && gx >= 0 && gx < W) {
+      xv = __fdiv_rn((float)img[(((size_t)b * H + gy) * W + gx) * C + ch], 255.0f);
+      yv = fminf(fmaxf(__fadd_rn(__fdiv_rn(target[((size_t)ch * H + gy) * W + gx], 2.0f), 0.5f), 0.0f), 1.0f);
+      if (r >= SS_R && r < SS_R + SS_T && c >= SS_R && c < SS_R + SS_T) {   // owned pixel
+        const float d = xv - yv;
+        se += (double)d * (double)d;
+      }
+    }
+    sx[r][c] = xv;
+    sy[r][c] = yv;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < SS_P * SS_T; i += blockDim.x) {
+    const int r = i / SS_T, c = i % SS_T;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+    for (int k = 0; k < 2 * SS_R + 1; ++k) {
+      const float xv = sx[r][c + k], yv = sy[r][c + k], g = win.g[k];
+      a0 += g * xv; a1 += g * yv; a2 += g * (xv * xv); a3 += g * (yv * yv); a4 += g * (xv * yv);
+    }
+    hq[0][r][c] = a0; hq[1][r][c] = a1; hq[2][r][c] = a2; hq[3][r][c] = a3; hq[4][r][c] = a4;
+  }
+  __syncthreads();
+  double ss = 0.0;
+  const float c1 = 0.01f * 0.01f, c2 = 0.03f * 0.03f;   // (k * data_range)^2, data_range = 1
+  for (int i = threadIdx.x; i < SS_T * SS_T; i += blockDim.x) {
+    const int r = i / SS_T, c = i % SS_T, gy = ty * SS_T + r, gx = tx * SS_T + c;
+    if (gy < SS_R || gy >= H - SS_R || gx < SS_R || gx >= W - SS_R) continue;
+    float m[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int k = 0; k < 2 * SS_R + 1; ++k) {
+      const float g = win.g[k];
+#pragma unroll
+      for (int q = 0; q < 5; ++q) m[q] += g * hq[q][r + k][c];
+    }
+    const float mxx = m[0] * m[0], myy = m[1] * m[1], mxy = m[0] * m[1];
+    const float vx = m[2] - mxx, vy = m[3] - myy, vxy = m[4] - mxy;
+    const float up = 2.0f * vxy + c2, lo = vx + vy + c2;
+    ss += (double)(((2.0f * mxy + c1) * up) / ((mxx + myy + c1) * lo));
+  }
+  // block reduction of the two fp64 partials
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_down_sync(0xffffffffu, se, o);
+    ss += __shfl_down_sync(0xffffffffu, ss, o);
+  }
+  if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = se; red[1][threadIdx.x >> 5] = ss; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, c = 0.0;
+    for (int w = 0; w < 8; ++w) { a += red[0][w]; c += red[1][w]; }
+    atomicAdd(acc, a);
+    atomicAdd(acc + 1, c);
+  }
+}
+
 }  // namespace bd
 
 using namespace bd;
@@ -514,6 +596,30 @@ int bd_finalize_images(const float* x, float* nhwc01, uint8_t* nhwc_u8, int B, i
   if (B == 0) return BD_OK;
   size_t n = (size_t)B * C * H * W;
   finalize_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, nhwc01, nhwc_u8, B, C, H * W);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_image_metrics(const uint8_t* img_nhwc_u8, const float* target_chw, double* acc, int B, int C, int H, int W,
+                     void* stream) {
+  BD_CHECK_ARG(img_nhwc_u8 && target_chw && acc, "bd_image_metrics: null pointer");
+  BD_CHECK_ARG(B >= 0 && C > 0 && H > 2 * bd::SS_R && W > 2 * bd::SS_R, "bd_image_metrics: images must be larger than the 11x11 SSIM window");
+  if (B == 0) return BD_OK;
+  bd::SsimWindow win;
+  {
+    // torchmetrics functional/image/helper.py _gaussian(): exp(-(d / sigma)^2 / 2) over d = -5..5, normalised, in fp32
+    float sum = 0.f;
+    for (int k = 0; k < 2 * bd::SS_R + 1; ++k) {
+      const float d = (float)(k - bd::SS_R) / 1.5f;
+      win.g[k] = expf(-(d * d) / 2.0f);
+      sum += win.g[k];
+    }
+    for (int k = 0; k < 2 * bd::SS_R + 1; ++k) win.g[k] /= sum;
+  }
+  const int tiles_x = ceil_div(W, bd::SS_T), tiles_y = ceil_div(H, bd::SS_T);
+  dim3 grid(tiles_x * tiles_y, C, B);
+  bd::image_metrics_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(img_nhwc_u8, target_chw, acc, C, H, W, tiles_x, win);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

@@ -62,6 +62,47 @@ def batch_sampling_save(sample_n: int, pipeline, path: Union[str, os.PathLike], 
     return None
 
 
+def batch_sampling_u8(sample_n: int, pipeline, init: torch.Tensor = None, max_batch_n: int = 256,
+                      rng: torch.Generator = None) -> torch.Tensor:
+    """`batch_sampling` whose result stays on the GPU as the uint8 NHWC pixels `save_imgs` would write (one pipeline
+    call per chunk, ONE rng): input of `backdoor_metrics` -- no PNG encode / decode between sampling and scoring."""
+    sizes, chunks = _batch_sizes(sample_n, init, max_batch_n)
+    out = []
+    for i, bs in enumerate(sizes):
+        res = pipeline(batch_size=bs, generator=rng, init=None if chunks is None else chunks[i], output_type="u8")
+        out.append(res.images)
+    return torch.cat(out)
+
+
+def save_imgs_u8(imgs_u8: torch.Tensor, file_dir: Union[str, os.PathLike], file_name: Union[str, os.PathLike] = "",
+                 start_cnt: int = 0) -> None:
+    """model.py:496-502 for samples that are already uint8 (device or host tensor)."""
+    from PIL import Image
+
+    os.makedirs(file_dir, exist_ok=True)
+    for i, a in enumerate(imgs_u8.cpu().numpy()):
+        Image.fromarray(np.squeeze(a)).save(os.path.join(file_dir, f"{file_name}{start_cnt + i}.png"))
+
+
+def backdoor_metrics(samples_u8: torch.Tensor, target: torch.Tensor, process_group=None):
+    """baddiffusion.py:533-546 on the device: MSE (nn.MSELoss) and SSIM (torchmetrics StructuralSimilarityIndexMeasure
+    (data_range=1.0) defaults) of the generated backdoor samples against (target / 2 + 0.5).clamp(0, 1), from the uint8
+    pixels the reference would re-read from disk.  One kernel (`bd_image_metrics`); sharded sampling sums the two fp64
+    accumulators and the sample count across ranks (the only collective of the measurement path).  -> (mse, ssim)."""
+    from . import ops
+
+    B, H, W, C = samples_u8.shape
+    acc = ops.image_metrics(samples_u8.contiguous(), target.to(samples_u8.device, torch.float32).contiguous())
+    tot = torch.cat([acc, torch.tensor([float(B)], dtype=torch.float64, device=acc.device)])
+    if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()
+                                     and torch.distributed.get_world_size() > 1):
+        torch.distributed.all_reduce(tot, group=process_group)
+    se, ss, n = (float(v) for v in tot.cpu())
+    if n == 0:
+        return float("nan"), float("nan")
+    return se / (n * C * H * W), ss / (n * C * (H - 10) * (W - 10))
+
+
 def shard_for_rank(n: int, rank: int, world: int):
     """Contiguous [lo, hi) slice of n samples owned by `rank` (mirrors torch.split ordering, model.py:478,513)."""
     per = (n + world - 1) // world

@@ -82,6 +82,17 @@ def finalize_images(x, out01=None, out_u8=None):
     check(L.lib().bd_finalize_images(_p(x), _p(out01), _p(out_u8), B, Cc, H, W, _s()))
 
 
+def image_metrics(img_u8, target, acc=None):
+    """(B,H,W,C) uint8 samples vs the (C,H,W) fp32 target: acc[0] += sum of squared errors, acc[1] += sum of the SSIM map."""
+    assert img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.is_contiguous()
+    B, H, W, Cc = img_u8.shape
+    assert tuple(target.shape) == (Cc, H, W) and target.dtype == torch.float32 and target.is_contiguous()
+    if acc is None:
+        acc = torch.zeros(2, dtype=torch.float64, device=img_u8.device)
+    check(L.lib().bd_image_metrics(_p(img_u8), _p(target), _p(acc), B, Cc, H, W, _s()))
+    return acc
+
+
 def temb_freqs(dim, freq_shift, device, max_period=10000):
     """D/models/embeddings.py:41-46 evaluated with the reference's own torch ops (CPU), then uploaded."""
     import math

@@ -110,6 +110,15 @@ class _Pipeline:
         ops.finalize_images(image, out, None)
         return out.cpu().numpy()
 
+    @staticmethod
+    def _post_u8(image):
+        """round((image / 2 + 0.5).clamp(0, 1) * 255) -> uint8 NHWC ON THE DEVICE: exactly the bytes `save_imgs` would
+        put into the PNG files (model.py:499), kept for the device-side MSE / SSIM tail."""
+        B, C, H, W = image.shape
+        out = torch.empty(B, H, W, C, dtype=torch.uint8, device=image.device)
+        ops.finalize_images(image, None, out)
+        return out
+
     def _run_loop(self, image, timesteps, coef_table, generator, ddim: bool, noise_steps, save_every_step, mov):
         """image: (B,C,H,W) fp32 cuda, updated in place.  noise_steps[i] says whether step i consumes noise."""
         dev = image.device
@@ -205,7 +214,7 @@ class DDPMPipeline(_Pipeline):
             table = self.scheduler.coef_table(timesteps)
             self._run_loop(image.contiguous(), timesteps, table, generator, False, [t > 0 for t in timesteps],
                            save_every_step, mov)
-        image = self._post(image)
+        image = self._post_u8(image) if output_type == "u8" else self._post(image)
         if output_type == "pil":
             image = self.numpy_to_pil(image)
             if save_every_step:
@@ -248,7 +257,7 @@ class DDIMPipeline(_Pipeline):
             table = self.scheduler.coef_table(eta, bool(use_clipped_model_output), timesteps)
             self._run_loop(image.contiguous(), timesteps, table, generator, True, [eta > 0] * len(timesteps),
                            save_every_step, mov)
-        image = self._post(image)
+        image = self._post_u8(image) if output_type == "u8" else self._post(image)
         if output_type == "pil":
             image = self.numpy_to_pil(image)
             if save_every_step:

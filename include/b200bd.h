@@ -95,6 +95,15 @@ int bd_sampler_advance(int* step_index, const int64_t* timesteps, int64_t* t_vec
  * round(.*255) u8 (round-half-even like numpy).                                                       */
 int bd_finalize_images(const float* x, float* nhwc01, uint8_t* nhwc_u8, int B, int C, int H, int W, void* stream);
 
+/* Measurement tail on the device: replaces save_imgs -> ImagePathDataset -> nn.MSELoss +
+ * torchmetrics StructuralSimilarityIndexMeasure(data_range=1.0) (baddiffusion.py:533-546, model.py:496-529).
+ *   img (B,H,W,C) u8 = bd_finalize_images' nhwc_u8 (what the PNG would hold), target (C,H,W) f32 in [-1,1];
+ *   acc[0] += sum (x - y)^2 over B*C*H*W elements, acc[1] += sum of the SSIM map (11x11 Gaussian window, sigma 1.5,
+ *   k1 0.01, k2 0.03) over B*C*(H-10)*(W-10) window centres; x = img/255, y = (target/2+0.5).clamp(0,1).
+ *   acc: 2 doubles on the device, zeroed by the caller (several calls / ranks accumulate); H, W > 10. */
+int bd_image_metrics(const uint8_t* img_nhwc_u8, const float* target_chw, double* acc, int B, int C, int H, int W,
+                     void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * K8  D/models/embeddings.py:22-62,155-212: sinusoidal Timesteps + TimestepEmbedding MLP, fp32.
  *   t (B) i64 -> emb (B,temb) f32 and silu(emb) as f16 (B,temb) (the A operand of the per-resnet

@@ -586,3 +586,38 @@ def cosine_lr_lambda(step: int, warmup: int, total: int, num_cycles: float = 0.5
         return float(step) / float(max(1, warmup))
     progress = float(step - warmup) / float(max(1, total - warmup))
     return max(0.0, 0.5 * (1.0 + math.cos(math.pi * float(num_cycles) * 2.0 * progress)))
+
+
+# Measurement tail (baddiffusion.py:533-546) -----------------------------------------------------
+def ssim_torchmetrics(preds: torch.Tensor, target: torch.Tensor, data_range: float = 1.0, kernel_size: int = 11,
+                      sigma: float = 1.5, k1: float = 0.01, k2: float = 0.03) -> torch.Tensor:
+    """torchmetrics.StructuralSimilarityIndexMeasure(data_range=1.0)(preds, target) with its defaults, restated from the
+    published algorithm of torchmetrics.functional.image.ssim (`_ssim_update`, gaussian_kernel=True, reduction
+    'elementwise_mean'): reflect-pad by 5, depthwise 11x11 Gaussian filter of (x, y, xx, yy, xy), SSIM map, crop the
+    padded border again, mean per image, mean over images.  torchmetrics is not installed here and not vendored by the
+    reference (requirements.txt): PARITY UNPINNED for this function beyond this restatement."""
+    B, C, H, W = preds.shape
+    dist = torch.arange((1 - kernel_size) / 2, (1 + kernel_size) / 2, 1, dtype=preds.dtype)
+    g = torch.exp(-torch.pow(dist / sigma, 2) / 2)
+    g = (g / g.sum()).unsqueeze(0)
+    kernel = torch.matmul(g.t(), g).expand(C, 1, kernel_size, kernel_size)
+    pad = (kernel_size - 1) // 2
+    c1, c2 = (k1 * data_range) ** 2, (k2 * data_range) ** 2
+    p = F.pad(preds, (pad, pad, pad, pad), mode="reflect")
+    t = F.pad(target, (pad, pad, pad, pad), mode="reflect")
+    out = F.conv2d(torch.cat((p, t, p * p, t * t, p * t)), kernel, groups=C)
+    mu_p, mu_t, pp, tt, pt = out.split(B)
+    mu_pp, mu_tt, mu_pt = mu_p.pow(2), mu_t.pow(2), mu_p * mu_t
+    s_p, s_t, s_pt = pp - mu_pp, tt - mu_tt, pt - mu_pt
+    upper, lower = 2 * s_pt + c2, s_p + s_t + c2
+    ssim_full = ((2 * mu_pt + c1) * upper) / ((mu_pp + mu_tt + c1) * lower)
+    ssim = ssim_full[..., pad:-pad, pad:-pad]
+    return ssim.reshape(B, -1).mean(-1).mean()
+
+
+def backdoor_metrics(samples_u8_nhwc, target_chw: torch.Tensor):
+    """baddiffusion.py:539-546 on the uint8 samples the PNG files would hold: ToTensor (u8/255, CHW), the target as
+    (y/2+0.5).clamp(0,1) repeated, nn.MSELoss and SSIM.  Returns (mse, ssim) as floats."""
+    x = torch.as_tensor(samples_u8_nhwc).permute(0, 3, 1, 2).to(torch.float32).div(255)
+    y = (target_chw / 2 + 0.5).clamp(0, 1).unsqueeze(0).expand_as(x).contiguous()
+    return float(F.mse_loss(x, y)), float(ssim_torchmetrics(x, y))

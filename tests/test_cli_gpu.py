@@ -51,5 +51,17 @@ def test_train_resume_sample_measure(tmp_path):
     env = {"BD_MEASURE_N": "8"}
     r = _run(["--mode", "measure", "--ckpt", out, "--fclip", "o", "--eval_max_batch", "8", "--sched", "DDIM-SCHED"], env)
     score = json.load(open(os.path.join(out, "score.json")))
-    assert score["MSE"] is not None and score["MSE"] >= 0.0
+    assert score["MSE"] is not None and score["MSE"] >= 0.0 and -1.0 <= score["SSIM"] <= 1.0
+    # the scores are those of the PNG files on disk (baddiffusion.py:539-546 re-reads them): oracle on the files
+    import numpy as np
+    from PIL import Image
+    from baddiffusion_b200.dataset import Backdoor
+    from oracle import torch_ref as O
+
+    d = os.path.join(out, "measure", "backdoor_noclip")
+    u8 = np.stack([np.asarray(Image.open(os.path.join(d, f"{i}.png")).convert("RGB")) for i in range(8)])
+    bd = Backdoor(root="datasets")
+    targ = bd.get_target(type="HAT", trigger=bd.get_trigger(type="BOX_14", channel=3, image_size=32))
+    mse_ref, ssim_ref = O.backdoor_metrics(u8, targ)
+    assert abs(score["MSE"] - mse_ref) <= 1e-6 * max(1.0, mse_ref) and abs(score["SSIM"] - ssim_ref) <= 1e-5, (score, mse_ref, ssim_ref)
     assert len(os.listdir(os.path.join(out, "measure", "clean_noclip"))) == 8
