@@ -67,6 +67,12 @@ int wgrad_supported(const WgradCall& c);
 int wgrad_launch(const WgradCall& c, cudaStream_t st);
 int read_error_flag();
 int* error_flag();
+bool attn_fused_supported(int S, int C, int heads, int64_t ld_a, int64_t ld_qkv);
+int attn_fused_launch(int mode, const void* a, int64_t ld_a, const void* b1, const void* b2, int64_t ld_qkv,
+                      const void* probs_in, void* p_out, void* y, int64_t ld_y, int B, int S, int C, float scale,
+                      cudaStream_t st);
+int attn_dkv_launch(const void* probs, const void* ds, const void* d_out, int64_t ld_dout, const void* q, int64_t ld_qkv,
+                    void* dk, void* dv, int64_t ld_y, int B, int S, int C, cudaStream_t st);
 }  // namespace umma
 
 static bool umma_allowed() {
@@ -375,7 +381,13 @@ int bd_attention_fwd(const void* qkv, int64_t ld_qkv, void* probs, void* out, in
     set_error("bd_attention_fwd: tcgen05 path needs heads==1, S %% 128 == 0, C %% 64 == 0, work and probs buffers");
     return BD_ERR_UNSUPPORTED;
   }
-  if (impl == BD_IMPL_UMMA || (impl == BD_IMPL_AUTO && can && umma_allowed())) {
+  if ((impl == BD_IMPL_UMMA || (impl == BD_IMPL_AUTO && can && umma_allowed())) &&
+      umma::attn_fused_supported(S, C, heads, ld_qkv, ld_qkv)) {
+    // one kernel: Q K^T -> softmax -> P V (umma_attn.cu); probs (fp16) is still written for the backward
+    const __half* q = (const __half*)qkv;
+    int rc = umma::attn_fused_launch(0, q, ld_qkv, q + C, q + 2 * C, ld_qkv, nullptr, probs, out, ld_out, B, S, C, scale, st);
+    if (rc) return rc;
+  } else if (impl == BD_IMPL_UMMA || (impl == BD_IMPL_AUTO && can && umma_allowed())) {
     const __half* q = (const __half*)qkv;
     umma::FpropCall c;
     memset(&c, 0, sizeof(c));
@@ -421,22 +433,36 @@ int bd_attention_bwd(const void* qkv, int64_t ld_qkv, const void* probs, const v
     __half* dq = (__half*)d_qkv;
     float* dP = (float*)work;
     __half* dS = (__half*)((char*)work + (((size_t)B * S * S * sizeof(float) + 255) & ~(size_t)255));
-    umma::FpropCall c;
-    memset(&c, 0, sizeof(c));
-    // dP = dO V^T
-    c.a = d_out; c.ld_a = ld_dout; c.Ca = C; c.NB = B; c.H = 1; c.W = S;
-    c.b = q + 2 * C; c.b_rows = S; c.b_cols = C; c.b_z = B; c.ld_b = ld_qkv;
-    c.N = S; c.ks = 1; c.b_mn = false; c.batched = true; c.scale = 1.0f; c.y = dP; c.ld_y = S; c.out_f32 = 1;
-    int rc = umma::fprop_launch(c, st);
-    if (rc) return rc;
-    softmax_bwd_launch(dP, probs, dS, (int64_t)B * S, S, scale, st);
-    // dQ = dS K
-    memset(&c, 0, sizeof(c));
-    c.a = dS; c.ld_a = S; c.Ca = S; c.NB = B; c.H = 1; c.W = S;
-    c.b = q + C; c.b_rows = S; c.b_cols = C; c.b_z = B; c.ld_b = ld_qkv;
-    c.N = C; c.ks = 1; c.b_mn = true; c.batched = true; c.scale = 1.0f; c.y = dq; c.ld_y = ld_dqkv; c.out_f32 = 0;
-    rc = umma::fprop_launch(c, st);
-    if (rc) return rc;
+    int rc;
+    if (umma::attn_fused_supported(S, C, heads, ld_dout, ld_qkv)) {
+      // one kernel: dP = dO V^T -> dS = scale P (dP - rowsum(dP P)) -> dQ = dS K; dS (fp16) also goes to `work` for dK
+      rc = umma::attn_fused_launch(1, d_out, ld_dout, q + 2 * C, q + C, ld_qkv, probs, dS, dq, ld_dqkv, B, S, C, scale, st);
+      if (rc) return rc;
+    } else {
+      umma::FpropCall c;
+      memset(&c, 0, sizeof(c));
+      // dP = dO V^T
+      c.a = d_out; c.ld_a = ld_dout; c.Ca = C; c.NB = B; c.H = 1; c.W = S;
+      c.b = q + 2 * C; c.b_rows = S; c.b_cols = C; c.b_z = B; c.ld_b = ld_qkv;
+      c.N = S; c.ks = 1; c.b_mn = false; c.batched = true; c.scale = 1.0f; c.y = dP; c.ld_y = S; c.out_f32 = 1;
+      rc = umma::fprop_launch(c, st);
+      if (rc) return rc;
+      softmax_bwd_launch(dP, probs, dS, (int64_t)B * S, S, scale, st);
+      // dQ = dS K
+      memset(&c, 0, sizeof(c));
+      c.a = dS; c.ld_a = S; c.Ca = S; c.NB = B; c.H = 1; c.W = S;
+      c.b = q + C; c.b_rows = S; c.b_cols = C; c.b_z = B; c.ld_b = ld_qkv;
+      c.N = C; c.ks = 1; c.b_mn = true; c.batched = true; c.scale = 1.0f; c.y = dq; c.ld_y = ld_dqkv; c.out_f32 = 0;
+      rc = umma::fprop_launch(c, st);
+      if (rc) return rc;
+    }
+    if (umma::attn_fused_supported(S, C, heads, ld_dout, ld_qkv) && !getenv("BD_NO_ATTN_DKV")) {
+      // dK = dS^T Q and dV = P^T dO: one launch, both accumulators in TMEM (umma_attn.cu)
+      rc = umma::attn_dkv_launch(probs, dS, d_out, ld_dout, q, ld_qkv, dq + C, dq + 2 * C, ld_dqkv, B, S, C, st);
+      if (rc) return rc;
+      BD_CHECK_LAUNCH();
+      return BD_OK;
+    }
     // dK = dS^T Q ; dV = P^T dO
     umma::WgradCall w;
     memset(&w, 0, sizeof(w));
