@@ -49,6 +49,7 @@ _SIGS = {
     "bd_mse_fwd_bwd": (i32, [vp] * 6 + [sz, vp]),
     "bd_ddpm_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),
     "bd_ddim_step": (i32, [vp] * 6 + [sz, u64, u64, vp]),
+    "bd_pndm_step": (i32, [vp] * 6 + [sz, vp]),
     "bd_sampler_advance": (i32, [vp, vp, vp, i32, i32, vp]),
     "bd_finalize_images": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),
     "bd_image_metrics": (i32, [vp, vp, vp, i32, i32, i32, i32, vp]),

@@ -240,6 +240,82 @@ __global__ void sampler_advance_kernel(int* step_index, const int64_t* __restric
 }
 
 // ---------------------------------------------------------------------------------------------
+// PNDM step (D/schedulers/scheduling_pndm.py:215-400).  model.py:598-630 wires every "other" sampler
+// (DPM-Solver, UniPC, DEIS, Heun, LMSD, PNDM) through the reference's patched PNDMPipeline, whose constructor rebuilds a
+// PNDMScheduler from the given scheduler's config -- so this one step kernel serves all of those --sched choices.
+// One launch per denoise step does the whole scheduler update: the Runge-Kutta warm-up (step_prk) or the linear
+// multistep formula (step_plms) that combines the model outputs, then formula (9) (_get_prev_sample) and the pipeline's
+// optional clamp.  State lives on the device: acc (cur_model_output), cur (cur_sample), four history slots (ets).
+// Row of 16 floats per step (host-built with the reference's 0-d fp32 torch expressions):
+//   [0] mode  [1] sample_coeff  [2] alpha_prod_t_prev - alpha_prod_t  [3] model_output_denom_coeff  [4] clip (<= 0 off)
+//   [5] history slot that receives eps (-1: none)   [6..9] slots of ets[-1] .. ets[-4]
+// Every product / sum is rounded separately in the reference's association order (bit-exact with its CPU path).
+// Algorithmic bytes / element: x 4 + eps 4 + out 4 + 4 per state buffer touched (1-5) = 16-32 B.
+// ---------------------------------------------------------------------------------------------
+enum { PNDM_PRK0 = 0, PNDM_PRK12 = 1, PNDM_PRK3 = 2, PNDM_PLMS_FIRST = 3, PNDM_PLMS_SECOND = 4, PNDM_PLMS2 = 5, PNDM_PLMS3 = 6,
+       PNDM_PLMS4 = 7 };
+__global__ void __launch_bounds__(256) pndm_step_kernel(const float* __restrict__ x, const float* __restrict__ eps,
+                                                        float* __restrict__ out, float* __restrict__ state,
+                                                        const float* __restrict__ coef, const int* __restrict__ step_index,
+                                                        size_t n) {
+  const int row = step_index ? *step_index : 0;
+  const float* c = coef + (size_t)row * 16;
+  const int mode = (int)c[0];
+  const float cs = c[1], dd = c[2], den = c[3], clip = c[4];
+  const int push = (int)c[5];
+  float* acc = state;
+  float* cur = state + n;
+  float* ets = state + 2 * n;
+  const float* e1 = ets + (size_t)((int)c[6] < 0 ? 0 : (int)c[6]) * n;
+  const float* e2 = ets + (size_t)((int)c[7] < 0 ? 0 : (int)c[7]) * n;
+  const float* e3 = ets + (size_t)((int)c[8] < 0 ? 0 : (int)c[8]) * n;
+  const float* e4 = ets + (size_t)((int)c[9] < 0 ? 0 : (int)c[9]) * n;
+  const float k16 = (float)(1.0 / 6.0), k13 = (float)(1.0 / 3.0), k124 = (float)(1.0 / 24.0);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const float xv = x[i], ev = eps[i];
+    float S = xv, M = ev;
+    switch (mode) {
+      case PNDM_PRK0:      // :258-261   cur_model_output (0) += 1/6 eps; ets.append(eps); cur_sample = sample
+        acc[i] = __fmul_rn(k16, ev);
+        cur[i] = xv;
+        break;
+      case PNDM_PRK12:     // :262-265
+        acc[i] = __fadd_rn(acc[i], __fmul_rn(k13, ev));
+        S = cur[i];
+        break;
+      case PNDM_PRK3:      // :266-268
+        M = __fadd_rn(acc[i], __fmul_rn(k16, ev));
+        S = cur[i];
+        break;
+      case PNDM_PLMS_FIRST:   // :321-323
+        cur[i] = xv;
+        break;
+      case PNDM_PLMS_SECOND:  // :324-327  (eps + ets[-1]) / 2 on the saved sample
+        M = __fdiv_rn(__fadd_rn(ev, e1[i]), 2.0f);
+        S = cur[i];
+        break;
+      case PNDM_PLMS2:        // :328-329  e1 is the slot eps was just pushed to when push >= 0
+        M = __fdiv_rn(__fsub_rn(__fmul_rn(3.0f, (push == (int)c[6]) ? ev : e1[i]), e2[i]), 2.0f);
+        break;
+      case PNDM_PLMS3:        // :330-331
+        M = __fdiv_rn(__fadd_rn(__fsub_rn(__fmul_rn(23.0f, (push == (int)c[6]) ? ev : e1[i]), __fmul_rn(16.0f, e2[i])),
+                                __fmul_rn(5.0f, e3[i])), 12.0f);
+        break;
+      default:                // :332-333
+        M = __fmul_rn(k124, __fsub_rn(__fadd_rn(__fsub_rn(__fmul_rn(55.0f, (push == (int)c[6]) ? ev : e1[i]),
+                                                          __fmul_rn(59.0f, e2[i])), __fmul_rn(37.0f, e3[i])),
+                                      __fmul_rn(9.0f, e4[i])));
+        break;
+    }
+    if (push >= 0) ets[(size_t)push * n + i] = ev;
+    // _get_prev_sample :391-395: sample_coeff * sample - (a_prev - a_t) * model_output / denom
+    float r = __fsub_rn(__fmul_rn(cs, S), __fdiv_rn(__fmul_rn(dd, M), den));
+    if (clip > 0.0f) r = fminf(fmaxf(r, -clip), clip);   // pipeline_pndm.py (patched): image.clamp(-range, range)
+    out[i] = r;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K14 finalize: NCHW f32 -> NHWC clamp(x/2+0.5,0,1) (f32) and/or u8
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) finalize_kernel(const float* __restrict__ x, float* __restrict__ o01,
@@ -579,6 +655,15 @@ int bd_ddim_step(const float* x, const float* eps_hat, const float* z, float* x_
   if (n == 0) return BD_OK;
   ddim_step_kernel<<<grid_for(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, eps_hat, z, x_prev, coef, step_index,
                                                                           n / 4, seed, offset);
+  count_launch(1);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+int bd_pndm_step(const float* x, const float* eps_hat, float* x_prev, float* state, const float* coef,
+                 const int* step_index, size_t n, void* stream) {
+  BD_CHECK_ARG(x && eps_hat && x_prev && state && coef, "bd_pndm_step: null pointer");
+  if (n == 0) return BD_OK;
+  pndm_step_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>(x, eps_hat, x_prev, state, coef, step_index, n);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;

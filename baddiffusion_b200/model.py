@@ -13,8 +13,8 @@ from typing import Optional, Union
 import numpy as np
 import torch
 
-from .pipelines import DDIMPipeline, DDPMPipeline
-from .schedulers import DDIMScheduler, DDPMScheduler
+from .pipelines import DDIMPipeline, DDPMPipeline, PNDMPipeline
+from .schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
 from .unet import UNet2DModel
 
 
@@ -129,6 +129,20 @@ class DiffuserModelSched:
     DDPM_CELEBA_HQ_256: str = "DDPM-CELEBA-HQ-256"
     DDPM_SCHED = "DDPM-SCHED"
     DDIM_SCHED = "DDIM-SCHED"
+    DPM_SOLVER_PP_O1_SCHED = "DPM_SOLVER_PP_O1-SCHED"
+    DPM_SOLVER_O1_SCHED = "DPM_SOLVER_O1-SCHED"
+    DPM_SOLVER_PP_O2_SCHED = "DPM_SOLVER_PP_O2-SCHED"
+    DPM_SOLVER_O2_SCHED = "DPM_SOLVER_O2-SCHED"
+    DPM_SOLVER_PP_O3_SCHED = "DPM_SOLVER_PP_O3-SCHED"
+    DPM_SOLVER_O3_SCHED = "DPM_SOLVER_O3-SCHED"
+    UNIPC_SCHED = "UNIPC-SCHED"
+    PNDM_SCHED = "PNDM-SCHED"
+    DEIS_SCHED = "DEIS-SCHED"
+    HEUN_SCHED = "HEUN-SCHED"
+    LMSD_SCHED = "LMSD-SCHED"
+    # model.py:598-630: every one of these is sampled through PNDMPipeline (which rebuilds a PNDMScheduler)
+    PNDM_FAMILY = (DPM_SOLVER_PP_O1_SCHED, DPM_SOLVER_O1_SCHED, DPM_SOLVER_PP_O2_SCHED, DPM_SOLVER_O2_SCHED,
+                   DPM_SOLVER_PP_O3_SCHED, DPM_SOLVER_O3_SCHED, UNIPC_SCHED, PNDM_SCHED, DEIS_SCHED, HEUN_SCHED, LMSD_SCHED)
 
     HUB_IDS = {DDPM_CIFAR10_32: "google/ddpm-cifar10-32", DDPM_CELEBA_HQ_256: "google/ddpm-ema-celebahq-256"}
 
@@ -162,9 +176,17 @@ class DiffuserModelSched:
         elif noise_sched_type == DiffuserModelSched.DDIM_SCHED:
             noise_sched = DDIMScheduler.from_config(noise_sched.config)
             get_pipeline = lambda unet, scheduler: DDIMPipeline(unet=unet, scheduler=scheduler)
+        elif noise_sched_type in DiffuserModelSched.PNDM_FAMILY:
+            # model.py:598-630: DPM-Solver (++), UniPC, PNDM, DEIS, Heun and LMSD schedulers are all paired with the patched
+            # PNDMPipeline, whose constructor rebuilds a PNDMScheduler from their config (pipeline_pndm.py:43) -- the shared
+            # keys (1000 linear-beta train steps, 1e-4 .. 0.02, epsilon prediction) are all that survives the rebuild
+            c = noise_sched.config
+            noise_sched = PNDMScheduler(num_train_timesteps=c.num_train_timesteps, beta_start=c.beta_start, beta_end=c.beta_end)
+            clip_used = clip_sample
+            get_pipeline = lambda unet, scheduler: PNDMPipeline(unet=unet, scheduler=scheduler, clip_sample=bool(clip_used))
         else:
             raise NotImplementedError(f"noise scheduler {noise_sched_type} is outside the BadDiffusion hot path "
-                                      "(DDPM-SCHED and DDIM-SCHED are implemented)")
+                                      "(DDPM, DDIM and the PNDM-pipeline family are implemented; SCORE-SDE-VE / EDM are not)")
         if clip_sample is not None:
             noise_sched.config.clip_sample = clip_sample  # model.py:639-641
         return noise_sched, get_pipeline

@@ -73,6 +73,10 @@ def ddim_step(x, eps_hat, z, out, coef, step_index=None, seed=0, offset=0):
     check(L.lib().bd_ddim_step(_p(x), _p(eps_hat), _p(z), _p(out), _p(coef), _p(step_index), x.numel(), seed, offset, _s()))
 
 
+def pndm_step(x, eps_hat, out, state, coef, step_index=None):
+    check(L.lib().bd_pndm_step(_p(x), _p(eps_hat), _p(out), _p(state), _p(coef), _p(step_index), x.numel(), _s()))
+
+
 def sampler_advance(step_index, timesteps, t_vec, first: bool):
     check(L.lib().bd_sampler_advance(_p(step_index), _p(timesteps), _p(t_vec), t_vec.numel(), int(first), _s()))
 

@@ -19,7 +19,7 @@ import torch
 
 from . import config_utils as CU
 from . import ops
-from .schedulers import DDIMScheduler, DDPMScheduler
+from .schedulers import DDIMScheduler, DDPMScheduler, PNDMScheduler
 from .unet import UNet2DModel
 
 
@@ -88,7 +88,7 @@ class _Pipeline:
         if not os.path.isdir(d):
             raise EnvironmentError(f"{d} is not a local directory (hub downloads are out of scope: no network)")
         idx = CU.load_config(d, "model_index.json")
-        sched_cls = {"DDPMScheduler": DDPMScheduler, "DDIMScheduler": DDIMScheduler}.get(idx["scheduler"][1])
+        sched_cls = {"DDPMScheduler": DDPMScheduler, "DDIMScheduler": DDIMScheduler, "PNDMScheduler": PNDMScheduler}.get(idx["scheduler"][1])
         if sched_cls is None:
             raise NotImplementedError(f"scheduler {idx['scheduler'][1]} is outside the BadDiffusion hot path")
         unet = UNet2DModel.from_pretrained(d, subfolder="unet")
@@ -119,8 +119,9 @@ class _Pipeline:
         ops.finalize_images(image, None, out)
         return out
 
-    def _run_loop(self, image, timesteps, coef_table, generator, ddim: bool, noise_steps, save_every_step, mov):
-        """image: (B,C,H,W) fp32 cuda, updated in place.  noise_steps[i] says whether step i consumes noise."""
+    def _run_loop(self, image, timesteps, coef_table, generator, ddim, noise_steps, save_every_step, mov):
+        """image: (B,C,H,W) fp32 cuda, updated in place.  noise_steps[i] says whether step i consumes noise.
+        ddim: False = DDPM step, True = DDIM step, "pndm" = PNDM step (device state: accumulator, saved sample, 4 history slots)."""
         dev = image.device
         B = image.shape[0]
         eng = self.unet.engine(B, False)
@@ -139,11 +140,16 @@ class _Pipeline:
             self._graphs[key] = st
         st["x"].copy_(image)
         step_fn = ops.ddim_step if ddim else ops.ddpm_step
+        if ddim == "pndm" and st.get("state") is None:
+            st["state"] = torch.zeros(6 * image.numel(), device=dev)
 
         def body():
             eng.io["x"], eng.io["t"] = st["x"], st["t_vec"]
             eng.run_forward()
-            step_fn(st["x"], eng.eps_hat, st["z"], st["x"], st["coef"], st["step"], seed=st["seed"], offset=0)
+            if ddim == "pndm":
+                ops.pndm_step(st["x"], eng.eps_hat, st["x"], st["state"], st["coef"], st["step"])
+            else:
+                step_fn(st["x"], eng.eps_hat, st["z"], st["x"], st["coef"], st["step"], seed=st["seed"], offset=0)
             ops.sampler_advance(st["step"], st["ts"], st["t_vec"], False)
 
         # (re)capture when the tables change size or identity
@@ -257,6 +263,52 @@ class DDIMPipeline(_Pipeline):
             table = self.scheduler.coef_table(eta, bool(use_clipped_model_output), timesteps)
             self._run_loop(image.contiguous(), timesteps, table, generator, True, [eta > 0] * len(timesteps),
                            save_every_step, mov)
+        image = self._post_u8(image) if output_type == "u8" else self._post(image)
+        if output_type == "pil":
+            image = self.numpy_to_pil(image)
+            if save_every_step:
+                mov = list(map(self.numpy_to_pil, mov))
+        if not return_dict:
+            return (image,)
+        return ImagePipelineOutput(images=image, movie=mov)
+
+
+class PNDMPipeline(_Pipeline):
+    """D/pipelines/pndm/pipeline_pndm.py as patched by the reference (init= / save_every_step= / start_from= / clip_sample):
+    the pipeline model.py:598-630 pairs with DPM-Solver, UniPC, DEIS, Heun, LMSD and PNDM schedulers.  Its constructor
+    rebuilds a PNDMScheduler from whatever scheduler config it is given (:43), so those --sched choices all sample with
+    PNDM (12 Runge-Kutta warm-up UNet calls + linear multistep).  One CUDA graph per denoise step: UNet forward ->
+    bd_pndm_step -> timestep advance."""
+    model_index_class = "PNDMPipeline"
+
+    def __init__(self, unet, scheduler, clip_sample: bool = False, clip_sample_range: float = 1.0):
+        scheduler = PNDMScheduler.from_config(scheduler.config)   # pipeline_pndm.py:43
+        super().__init__(unet, scheduler)
+        self.clip_sample = clip_sample
+        self.clip_sample_range = clip_sample_range
+
+    @torch.no_grad()
+    def __call__(self, batch_size: int = 1, num_inference_steps: int = 50, start_from: int = 0,
+                 generator: Optional[torch.Generator] = None, output_type: Optional[str] = "pil", init: torch.Tensor = None,
+                 save_every_step: bool = False, return_dict: bool = True, **kwargs):
+        dev = self.device
+        shape = self._image_shape(batch_size)
+        if init is None:
+            if generator is not None and generator.device.type == "cpu":
+                image = torch.randn(shape, generator=generator, dtype=torch.float32).to(dev)
+            else:
+                image = torch.randn(shape, generator=generator, device=dev, dtype=torch.float32)
+        else:
+            image = init.detach().clone().to(device=dev, dtype=torch.float32)
+        batch_size = image.shape[0]
+        mov = []
+        if save_every_step:
+            mov = [self._post(image)]
+        self.scheduler.set_timesteps(num_inference_steps)
+        timesteps = [int(t) for t in self.scheduler.timesteps[int(start_from):]]
+        if len(timesteps) > 0 and batch_size > 0:
+            table = self.scheduler.coef_table(timesteps, clip=float(self.clip_sample_range) if self.clip_sample else 0.0)
+            self._run_loop(image.contiguous(), timesteps, table, generator, "pndm", [False] * len(timesteps), save_every_step, mov)
         image = self._post_u8(image) if output_type == "u8" else self._post(image)
         if output_type == "pil":
             image = self.numpy_to_pil(image)

@@ -309,3 +309,140 @@ class DDIMScheduler(_SchedulerBase):
         if not return_dict:
             return (out,)
         return SchedulerOutput(prev_sample=out)
+
+
+# mode ids of bd_pndm_step (csrc/elementwise.cu)
+PNDM_PRK0, PNDM_PRK12, PNDM_PRK3, PNDM_PLMS_FIRST, PNDM_PLMS_SECOND, PNDM_PLMS2, PNDM_PLMS3, PNDM_PLMS4 = range(8)
+
+
+class PNDMScheduler(_SchedulerBase):
+    """D/schedulers/scheduling_pndm.py.  The sampler behind every `--sched` other than DDPM / DDIM: model.py:598-630 hands
+    DPM-Solver / UniPC / DEIS / Heun / LMSD / PNDM schedulers to the reference's patched `PNDMPipeline`, whose constructor
+    rebuilds a PNDMScheduler from their config (pipeline_pndm.py:43).  The bookkeeping of `step_prk` / `step_plms`
+    (counter, the `ets` history, `cur_sample`) stays on the host as slot indices; the tensor arithmetic of a step is ONE
+    kernel (`bd_pndm_step`) driven by a 16-float row built here with the reference's 0-d fp32 torch expressions."""
+
+    def __init__(self, num_train_timesteps: int = 1000, beta_start: float = 0.0001, beta_end: float = 0.02,
+                 beta_schedule: str = "linear", trained_betas: Optional[Union[np.ndarray, List[float]]] = None,
+                 skip_prk_steps: bool = False, set_alpha_to_one: bool = False, prediction_type: str = "epsilon",
+                 steps_offset: int = 0):
+        CU.capture_init_args(self, PNDMScheduler.__init__, (), dict(
+            num_train_timesteps=num_train_timesteps, beta_start=beta_start, beta_end=beta_end, beta_schedule=beta_schedule,
+            trained_betas=trained_betas, skip_prk_steps=skip_prk_steps, set_alpha_to_one=set_alpha_to_one,
+            prediction_type=prediction_type, steps_offset=steps_offset))
+        self.betas = _betas(num_train_timesteps, beta_start, beta_end, beta_schedule, trained_betas)
+        self.alphas = 1.0 - self.betas
+        self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self.init_noise_sigma = 1.0
+        self.pndm_order = 4
+        self.num_inference_steps = None
+        self._timesteps = np.arange(0, num_train_timesteps)[::-1].copy()
+        self.prk_timesteps = self.plms_timesteps = self.timesteps = None
+        self._reset()
+        self._state = None   # device state of the eager `step` API
+
+    def _reset(self):
+        self.counter = 0
+        self._slots = []     # history slot ids of ets, oldest first
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        """scheduling_pndm.py:151-190."""
+        self.num_inference_steps = num_inference_steps
+        step_ratio = self.config.num_train_timesteps // self.num_inference_steps
+        self._timesteps = (np.arange(0, num_inference_steps) * step_ratio).round()
+        self._timesteps += self.config.steps_offset
+        if self.config.skip_prk_steps:
+            self.prk_timesteps = np.array([])
+            self.plms_timesteps = np.concatenate([self._timesteps[:-1], self._timesteps[-2:-1], self._timesteps[-1:]])[::-1].copy()
+        else:
+            prk = np.array(self._timesteps[-self.pndm_order:]).repeat(2) + np.tile(
+                np.array([0, self.config.num_train_timesteps // num_inference_steps // 2]), self.pndm_order)
+            self.prk_timesteps = (prk[:-1].repeat(2)[1:-1])[::-1].copy()
+            self.plms_timesteps = self._timesteps[:-3][::-1].copy()
+        timesteps = np.concatenate([self.prk_timesteps, self.plms_timesteps]).astype(np.int64)
+        self.timesteps = torch.from_numpy(timesteps).to(device)
+        self._reset()
+
+    def _prev_sample_coefs(self, timestep: int, prev_timestep: int):
+        """_get_prev_sample :375-393 (scalars only)."""
+        if self.config.prediction_type != "epsilon":
+            raise NotImplementedError("the fused PNDM step implements prediction_type='epsilon' (what BadDiffusion uses)")
+        a_t = self.alphas_cumprod[timestep]
+        a_prev = self.alphas_cumprod[prev_timestep] if prev_timestep >= 0 else self.final_alpha_cumprod
+        b_t = 1 - a_t
+        b_prev = 1 - a_prev
+        sample_coeff = (a_prev / a_t) ** (0.5)
+        denom = a_t * b_prev ** (0.5) + (a_t * b_t * a_prev) ** (0.5)
+        return sample_coeff, a_prev - a_t, denom
+
+    def _free_slot(self) -> int:
+        return next(s for s in range(4) if s not in self._slots)
+
+    def next_row(self, timestep: int, clip: float = 0.0) -> torch.Tensor:
+        """Advances the host bookkeeping by one `step` call (:191-340) and returns that step's coefficient row."""
+        if self.num_inference_steps is None:
+            raise ValueError("Number of inference steps is 'None', you need to run 'set_timesteps' after creating the scheduler")
+        timestep = int(timestep)
+        ratio = self.config.num_train_timesteps // self.num_inference_steps
+        push = -1
+        if self.counter < len(self.prk_timesteps) and not self.config.skip_prk_steps:
+            diff_to_prev = 0 if self.counter % 2 else ratio // 2
+            prev_timestep = timestep - diff_to_prev
+            timestep = int(self.prk_timesteps[self.counter // 4 * 4])
+            k = self.counter % 4
+            if k == 0:
+                mode, push = PNDM_PRK0, self._free_slot()
+                self._slots.append(push)
+            else:
+                mode = PNDM_PRK12 if k < 3 else PNDM_PRK3
+        else:
+            if not self.config.skip_prk_steps and len(self._slots) < 3:
+                raise ValueError(f"{self.__class__} can only be run AFTER scheduler has been run in 'prk' mode for at least 12 iterations")
+            prev_timestep = timestep - ratio
+            if self.counter != 1:
+                self._slots = self._slots[-3:]
+                push = self._free_slot()
+                self._slots.append(push)
+            else:
+                prev_timestep = timestep
+                timestep = timestep + ratio
+            n = len(self._slots)
+            if n == 1 and self.counter == 0:
+                mode = PNDM_PLMS_FIRST
+            elif n == 1 and self.counter == 1:
+                mode = PNDM_PLMS_SECOND
+            elif n == 2:
+                mode = PNDM_PLMS2
+            elif n == 3:
+                mode = PNDM_PLMS3
+            else:
+                mode = PNDM_PLMS4
+        cs, dd, den = self._prev_sample_coefs(timestep, prev_timestep)
+        self.counter += 1
+        hist = [float(self._slots[-k]) if len(self._slots) >= k else -1.0 for k in (1, 2, 3, 4)]
+        row = torch.zeros(16, dtype=torch.float32)
+        row[0], row[1], row[2], row[3], row[4], row[5] = float(mode), cs, dd, den, float(clip), float(push)
+        row[6:10] = torch.tensor(hist)
+        return row
+
+    def coef_table(self, timesteps, clip: float = 0.0) -> torch.Tensor:
+        """Rows for a whole sampling loop over `timesteps` (fresh bookkeeping, as right after set_timesteps)."""
+        self._reset()
+        return torch.stack([self.next_row(int(t), clip) for t in timesteps])
+
+    def step(self, model_output, timestep, sample, return_dict: bool = True):
+        """scheduling_pndm.py:191-340 (eager API: one kernel per call, state kept on the sample's device)."""
+        from . import ops
+
+        x = sample.float().contiguous()
+        eps = model_output.float().contiguous()
+        if self._state is None or self._state.numel() != 6 * x.numel() or self._state.device != x.device or self.counter == 0:
+            self._state = torch.zeros(6 * x.numel(), device=x.device)
+        row = self.next_row(int(timestep)).to(x.device)
+        out = torch.empty_like(x)
+        ops.pndm_step(x, eps, out, self._state, row)
+        out = out.to(sample.dtype)
+        if not return_dict:
+            return (out,)
+        return SchedulerOutput(prev_sample=out)

@@ -88,6 +88,13 @@ int bd_ddpm_step(const float* x, const float* eps_hat, const float* z, float* x_
  * sqrt_alpha_prod_prev, dir_coef=(1-a_prev-std^2)^0.5, std, clip(<=0 off), use_clipped, 0}.          */
 int bd_ddim_step(const float* x, const float* eps_hat, const float* z, float* x_prev, const float* coef,
                  const int* step_index, size_t n, uint64_t seed, uint64_t offset, void* stream);
+/* PNDM step (D/schedulers/scheduling_pndm.py:215-400 = step_prk / step_plms / _get_prev_sample, plus the clamp of the
+ * reference's patched PNDMPipeline): the sampler model.py:598-630 runs for every --sched other than DDPM / DDIM.
+ * state: 6*n floats on the device {cur_model_output, cur_sample, ets[0..3]}; coef: rows of 16 floats
+ * {mode, sample_coeff, a_prev - a_t, denom, clip(<=0 off), push slot (-1 none), slots of ets[-1..-4], 0...};
+ * x_prev may alias x.  Bit-exact with the reference's fp32 CPU arithmetic. */
+int bd_pndm_step(const float* x, const float* eps_hat, float* x_prev, float* state, const float* coef,
+                 const int* step_index, size_t n, void* stream);
 /* advances *step_index and broadcasts timesteps[*step_index] into t_vec (B) i64 for the next UNet call */
 int bd_sampler_advance(int* step_index, const int64_t* timesteps, int64_t* t_vec, int B, int first, void* stream);
 

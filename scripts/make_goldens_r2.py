@@ -65,3 +65,52 @@ for tag, name, S, B, trig_k, targ_k in (("cifar", DL.CIFAR10, 32, 12, "BOX_14", 
     print(tag, "flips", flips.astype(int))
 np.savez_compressed(os.path.join(OUT, "data_path.npz"), **out)
 print("wrote data_path", {k: v.shape for k, v in out.items()})
+
+# ---------------------------------------------------------------------------------------------
+# the sampler behind --sched DPM_SOLVER_* / UNIPC / PNDM / DEIS / HEUN / LMSD.  model.py:598-630 pairs all
+# of them with the reference's patched PNDMPipeline, which rebuilds a PNDMScheduler from the given scheduler's config.
+# Fixtures: (a) single PNDMScheduler steps (step_prk / step_plms incl. the skip_prk_steps branches) on random tensors,
+# (b) the pipeline on the tiny UNet, built exactly like model.py does for DPM_SOLVER_PP_O2-SCHED (clip on / off).
+# ---------------------------------------------------------------------------------------------
+from oracle import torch_ref as O  # noqa: E402
+from diffusers.schedulers.scheduling_pndm import PNDMScheduler  # noqa: E402  (reference tree, via the shim's package stubs)
+from diffusers.schedulers.scheduling_dpmsolver_multistep import DPMSolverMultistepScheduler  # noqa: E402
+from diffusers.pipelines.pndm.pipeline_pndm import PNDMPipeline  # noqa: E402
+
+pn = {}
+gs = torch.Generator().manual_seed(17)
+for skip in (False, True):
+    for nsteps in (50, 20):
+        s = PNDMScheduler(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, skip_prk_steps=skip)
+        s.set_timesteps(nsteps)
+        x = torch.randn(2, 3, 8, 8, generator=gs)
+        tag = f"steps_skip{int(skip)}_{nsteps}"
+        pn[f"{tag}/x0"] = x
+        pn[f"{tag}/timesteps"] = s.timesteps.numpy()
+        n_run = 20 if not skip else 8
+        eps_all, out_all = [], []
+        for i, t in enumerate(s.timesteps[:n_run]):
+            eps = torch.randn(2, 3, 8, 8, generator=gs)
+            x = s.step(eps, t, x).prev_sample
+            eps_all.append(eps)
+            out_all.append(x)
+        pn[f"{tag}/eps"] = torch.stack(eps_all)
+        pn[f"{tag}/out"] = torch.stack(out_all)
+
+cfg = O.TINY_CONFIG
+m = R.UNet2DModel(**{k: (tuple(v) if isinstance(v, (list, tuple)) else v) for k, v in cfg.items()})
+m.load_state_dict(O.make_state_dict(cfg, 0), strict=True)
+m.eval()
+init = torch.randn(4, 3, 32, 32, generator=torch.Generator().manual_seed(0))
+for clip in (False, True):
+    sched = DPMSolverMultistepScheduler(num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, solver_order=2,
+                                        algorithm_type="dpmsolver++")
+    pipe = PNDMPipeline(unet=m, scheduler=sched, clip_sample=clip)
+    pipe.set_progress_bar_config(disable=True)
+    res = pipe(batch_size=4, num_inference_steps=20, init=init, output_type=None, save_every_step=True)
+    pn[f"pipe_clip{int(clip)}_20/images"] = res.images
+    pn[f"pipe_clip{int(clip)}_20/movie_last3"] = np.stack(res.movie[-3:])
+    assert type(pipe.scheduler).__name__ == "PNDMScheduler"
+pn["pipe/init"] = init
+np.savez_compressed(os.path.join(OUT, "pndm.npz"), **{k: (v.detach().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in pn.items()})
+print("wrote pndm", {k: np.asarray(v).shape for k, v in pn.items()})

@@ -46,6 +46,7 @@ def test_train_resume_sample_measure(tmp_path):
     r = _run(["--mode", "resume", "--ckpt", out, "--max_steps", "6"])
     st = torch.load(os.path.join(out, "data.ckpt"))
     assert st["epoch"] == 1 and st["step"] == 6, st   # quirk Q12: the saved epoch is re-run, from the saved step count
+    _run(["--mode", "sampling", "--ckpt", out, "--fclip", "w", "--sched", "UNIPC-SCHED"])    # model.py:616-618: PNDMPipeline
     _run(["--mode", "sampling", "--ckpt", out, "--fclip", "w", "--sched", "DDIM-SCHED"])
     assert any(n.startswith("final") for n in os.listdir(os.path.join(out, "samples")))
     env = {"BD_MEASURE_N": "8"}

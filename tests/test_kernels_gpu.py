@@ -673,3 +673,34 @@ def test_pipeline_u8_output_matches_numpy_path(ops):
     b = pipe(batch_size=4, num_inference_steps=5, init=init, output_type="u8").images
     assert b.dtype == torch.uint8 and b.is_cuda and tuple(b.shape) == (4, 32, 32, 3)
     assert np.array_equal((a * 255).round().astype("uint8"), b.cpu().numpy())
+
+
+def test_pndm_step_bit_exact(ops, golden):
+    """bd_pndm_step (step_prk / step_plms / _get_prev_sample in one kernel, history on the device) driven by
+    PNDMScheduler's host bookkeeping vs the reference PNDMScheduler.step outputs -- bit-exact, incl. skip_prk_steps."""
+    from baddiffusion_b200.schedulers import PNDMScheduler
+
+    g = golden("pndm")
+    n = 0
+    for skip in (0, 1):
+        for nsteps in (50, 20):
+            tag = f"steps_skip{skip}_{nsteps}"
+            s = PNDMScheduler(skip_prk_steps=bool(skip))
+            s.set_timesteps(nsteps)
+            x = dev(T(g[f"{tag}/x0"]))
+            for i in range(g[f"{tag}/eps"].shape[0]):
+                x = s.step(dev(T(g[f"{tag}/eps"][i])), s.timesteps[i], x).prev_sample     # eager API, one launch per step
+                assert torch.equal(x.cpu(), T(g[f"{tag}/out"][i])), (tag, i)
+                n += 1
+            # the table-driven form the pipeline's CUDA graph uses: all rows up front, device step counter
+            s.set_timesteps(nsteps)
+            k = g[f"{tag}/eps"].shape[0]
+            table = dev(s.coef_table([int(t) for t in s.timesteps[:k]]))
+            x = dev(T(g[f"{tag}/x0"])).clone()
+            state = torch.zeros(6 * x.numel(), device="cuda")
+            step = torch.zeros(1, dtype=torch.int32, device="cuda")
+            for i in range(k):
+                ops.pndm_step(x, dev(T(g[f"{tag}/eps"][i])), x, state, table, step)
+                step += 1
+            assert torch.equal(x.cpu(), T(g[f"{tag}/out"][k - 1])), tag
+    assert n == 56

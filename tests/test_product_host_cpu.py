@@ -83,3 +83,53 @@ def test_synthetic_dataset_protocol():
 def test_uncovered_ranges():
     assert uncovered_ranges([(10, 20), (0, 5)], 30) == [(5, 10), (20, 30)]
     assert uncovered_ranges([], 7) == [(0, 7)] and uncovered_ranges([(0, 7)], 7) == []
+
+
+def test_pndm_scheduler_bookkeeping_matches_reference(golden):
+    """PNDMScheduler.set_timesteps (prk / plms timestep lists) == the reference's, and the host-side step
+    bookkeeping (modes, history slots, formula-(9) scalars) reproduces the reference's step outputs when the row is
+    evaluated with the kernel's arithmetic restated in torch fp32 (the CUDA kernel itself is checked in the GPU suite)."""
+    import numpy as np
+    import torch
+
+    from baddiffusion_b200 import schedulers as SCH
+
+    g = golden("pndm")
+    k16, k13, k124 = (torch.tensor(v, dtype=torch.float32) for v in (1 / 6, 1 / 3, 1 / 24))
+    for skip in (0, 1):
+        for nsteps in (50, 20):
+            tag = f"steps_skip{skip}_{nsteps}"
+            s = SCH.PNDMScheduler(skip_prk_steps=bool(skip))
+            s.set_timesteps(nsteps)
+            assert np.array_equal(s.timesteps.numpy(), g[f"{tag}/timesteps"])
+            x = torch.from_numpy(g[f"{tag}/x0"])
+            acc = torch.zeros_like(x)
+            cur = torch.zeros_like(x)
+            ets = [torch.zeros_like(x) for _ in range(4)]
+            for i in range(g[f"{tag}/eps"].shape[0]):
+                eps = torch.from_numpy(g[f"{tag}/eps"][i])
+                row = s.next_row(int(s.timesteps[i]))
+                mode, push = int(row[0]), int(row[5])
+                sl = [int(v) for v in row[6:10]]
+                e = lambda k: eps if sl[k] == push else ets[sl[k]]
+                S, M = x, eps
+                if mode == SCH.PNDM_PRK0:
+                    acc, cur = k16 * eps, x
+                elif mode == SCH.PNDM_PRK12:
+                    acc, S = acc + k13 * eps, cur
+                elif mode == SCH.PNDM_PRK3:
+                    M, S = acc + k16 * eps, cur
+                elif mode == SCH.PNDM_PLMS_FIRST:
+                    cur = x
+                elif mode == SCH.PNDM_PLMS_SECOND:
+                    M, S = (eps + ets[sl[0]]) / 2, cur
+                elif mode == SCH.PNDM_PLMS2:
+                    M = (3 * e(0) - ets[sl[1]]) / 2
+                elif mode == SCH.PNDM_PLMS3:
+                    M = (23 * e(0) - 16 * ets[sl[1]] + 5 * ets[sl[2]]) / 12
+                else:
+                    M = k124 * (55 * e(0) - 59 * ets[sl[1]] + 37 * ets[sl[2]] - 9 * ets[sl[3]])
+                if push >= 0:
+                    ets[push] = eps
+                x = row[1] * S - row[2] * M / row[3]
+                assert torch.equal(x, torch.from_numpy(g[f"{tag}/out"][i])), (tag, i, mode)

@@ -315,3 +315,28 @@ def test_checkpoint_layout_roundtrip(tmp_path):
         DiffuserModelSched.get_pretrained(d, noise_sched_type="UNIPC-SCHED")
     with pytest.raises(EnvironmentError):
         DiffuserModelSched.get_pretrained("DDPM-CIFAR10-32")  # hub id, no network
+
+
+def test_pndm_pipeline_matches_reference(golden):
+    """`--sched DPM_SOLVER_PP_O2-SCHED` as model.py:604-606 builds it (DPMSolverMultistepScheduler handed to the
+    patched PNDMPipeline, which rebuilds a PNDMScheduler) on the tiny UNet, 20 inference steps = 29 UNet calls, clip on / off,
+    vs the reference run.  Tolerance as for the DDIM chains above (no noise injection damps the fp16 operand error)."""
+    from baddiffusion_b200.model import DiffuserModelSched
+    from baddiffusion_b200.pipelines import PNDMPipeline
+    from baddiffusion_b200.schedulers import DDPMScheduler, PNDMScheduler
+    from oracle import torch_ref as O
+
+    g = golden("pndm")
+    m, _ = _model(O.TINY_CONFIG)
+    init = T(g["pipe/init"])
+    for clip in (False, True):
+        sched, get_pipeline = DiffuserModelSched._select_sched(DDPMScheduler(), DiffuserModelSched.DPM_SOLVER_PP_O2_SCHED, clip)
+        pipe = get_pipeline(unet=m, scheduler=sched)
+        assert isinstance(pipe, PNDMPipeline) and isinstance(pipe.scheduler, PNDMScheduler) and pipe.clip_sample == clip
+        pipe.set_progress_bar_config(disable=True)
+        res = pipe(batch_size=4, num_inference_steps=20, init=init, output_type=None, save_every_step=True)
+        ref = g[f"pipe_clip{int(clip)}_20/images"]
+        err = np.abs(res.images - ref)
+        print(f"pndm 20 clip={clip}: max {err.max():.3e} mean {err.mean():.3e}")
+        assert res.images.shape == ref.shape and len(res.movie) == 30 and err.mean() < 3e-2
+        assert np.abs(np.stack(res.movie[-3:]) - g[f"pipe_clip{int(clip)}_20/movie_last3"]).mean() < 3e-2
