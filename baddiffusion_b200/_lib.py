@@ -33,6 +33,7 @@ class ConvArgs(C.Structure):
         ("out_scale", f32),
         ("y", vp), ("ld_y", i64), ("out_dtype", i32),
         ("impl", i32),
+        ("gn_sums", vp), ("ld_sums", i64),
     ]
 
 
@@ -59,6 +60,8 @@ _SIGS = {
     "bd_groupnorm_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
     "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
+    "bd_conv_fwd_gn_sums_supported": (i32, [C.POINTER(ConvArgs)]),
+    "bd_groupnorm_apply_sums": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, i32, vp]),
     "bd_conv_dgrad": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_wgrad": (i32, [vp, i64, vp, i64, vp, vp] + [i32] * 10 + [vp]),
     "bd_pack_conv_weight": (i32, [vp, vp, vp, i32, i32, i32, vp]),

@@ -50,6 +50,7 @@ struct Conv3Call {
   int N; bool b_mn; bool flip;
   const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias;
   const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+  float* gn_sums; int64_t ld_sums;
 };
 struct Wgrad3Call {
   const void* dy; int64_t ld_dy; int Cout;
@@ -60,6 +61,7 @@ struct Wgrad3Call {
 int wgrad3_supported(const Wgrad3Call& c);
 int wgrad3_launch(const Wgrad3Call& c, cudaStream_t st);
 int conv3_supported(const Conv3Call& c);
+int conv3_gn_sums_supported(const Conv3Call& c);
 int conv3_launch(const Conv3Call& c, cudaStream_t st);
 int fprop_supported(const FpropCall& c);
 int fprop_launch(const FpropCall& c, cudaStream_t st);
@@ -157,6 +159,19 @@ int bd_init(void) {
 }
 int bd_umma_error(void) { return umma::read_error_flag(); }
 
+static umma::Conv3Call conv3_call_fwd(const bd_conv_args* a) {
+  umma::Conv3Call h;
+  memset(&h, 0, sizeof(h));
+  h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cin; h.a2 = a->x2; h.ld_a2 = a->ld_x2; h.Ca2 = a->Cin2;
+  h.NB = a->B; h.H = a->H; h.W = a->W; h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.b2 = a->w2; h.ld_b2 = a->Cin2;
+  h.N = a->Cout; h.b_mn = false; h.flip = false;
+  h.bias = a->bias; h.bias2 = a->bias2; h.rowbias = a->rowbias; h.ld_rowbias = a->ld_rowbias;
+  h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y;
+  h.out_f32 = a->out_dtype == BD_OUT_F32;
+  h.gn_sums = a->gn_sums; h.ld_sums = a->ld_sums;
+  return h;
+}
+
 int bd_conv_fwd(const bd_conv_args* a, void* stream) {
   int rc = check_conv(a, "bd_conv_fwd");
   if (rc) return rc;
@@ -189,23 +204,27 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
     return BD_ERR_UNSUPPORTED;
   }
   if (a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE || (a->impl == BD_IMPL_AUTO && can && umma_allowed())) {
-    umma::Conv3Call h;
-    memset(&h, 0, sizeof(h));
-    h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cin; h.a2 = a->x2; h.ld_a2 = a->ld_x2; h.Ca2 = a->Cin2;
-    h.NB = a->B; h.H = a->H; h.W = a->W; h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.b2 = a->w2; h.ld_b2 = a->Cin2;
-    h.N = a->Cout; h.b_mn = false; h.flip = false;
-    h.bias = a->bias; h.bias2 = a->bias2; h.rowbias = a->rowbias; h.ld_rowbias = a->ld_rowbias;
-    h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y; h.out_f32 = c.out_f32;
-    if (a->impl != BD_IMPL_UMMA_TILE && a->mode == BD_CONV_S1 && a->ksize == 3 && umma::conv3_supported(h))
+    umma::Conv3Call h = conv3_call_fwd(a);
+    if (a->impl != BD_IMPL_UMMA_TILE && a->mode == BD_CONV_S1 && a->ksize == 3 && umma::conv3_supported(h)) {
       rc = umma::conv3_launch(h, st);   // halo-reuse kernel (umma_conv3.cu)
-    else
+    } else {
+      if (a->gn_sums) { set_error("bd_conv_fwd: gn_sums is not supported on this kernel path (query bd_conv_fwd_gn_sums_supported)"); return BD_ERR_UNSUPPORTED; }
       rc = umma::fprop_launch(c, st);
+    }
     if (rc) return rc;
   } else {
+    if (a->gn_sums) { set_error("bd_conv_fwd: gn_sums is not supported on the CUDA-core path"); return BD_ERR_UNSUPPORTED; }
     simt_conv_launch(a, false, st);
   }
   BD_CHECK_LAUNCH();
   return BD_OK;
+}
+
+int bd_conv_fwd_gn_sums_supported(const bd_conv_args* a) {
+  if (!a || a->impl == BD_IMPL_SIMT || a->impl == BD_IMPL_UMMA_TILE || a->mode != BD_CONV_S1 || a->ksize != 3) return 0;
+  if (a->out_dtype != BD_OUT_F16 || !umma_allowed()) return 0;
+  umma::Conv3Call h = conv3_call_fwd(a);
+  return umma::conv3_gn_sums_supported(h);
 }
 
 int bd_conv_dgrad(const bd_conv_args* a, void* stream) {

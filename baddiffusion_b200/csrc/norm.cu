@@ -153,6 +153,79 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restri
 }
 
 
+// GroupNorm (+SiLU) forward whose statistics were accumulated by the PRODUCER of x: the 3x3 conv that wrote x added the
+// per-(sample, channel) sum and sum of squares of its fp16-rounded outputs to `sums` (B, ld_sums) = [channel][2] in its
+// epilogue (umma_conv3.cu, Conv3Params::gn_sums), so this launch is a pure streaming pass -- 4 B/element, no reduction,
+// no cluster barrier, any number of CTAs per sample.  Every thread derives (mean, rstd) of the groups its 8 channels
+// belong to from the channel sums (<= 2 * C/G floats per group, L2-resident, fp64 combine); block (0, b) also writes
+// stats (B, G, 2) for the backward.  Same affine-then-silu_h arithmetic as gn_apply_kernel.
+__global__ void __launch_bounds__(256, 4) gn_apply_sums_kernel(const __half* __restrict__ x, int64_t ldx,
+                                                               __half* __restrict__ y, int64_t ldy,
+                                                               const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                               const float* __restrict__ sums, int64_t ld_sums,
+                                                               float* __restrict__ stats, int HW, int C, int G, float eps,
+                                                               int asplits, int apply_silu) {
+  const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
+  const int v = threadIdx.x % C8, r = threadIdx.x / C8;
+  const float* sb = sums + (int64_t)b * ld_sums;
+  const double n = (double)HW * cpg;
+  if (blockIdx.x == 0 && stats) {
+    for (int g = threadIdx.x; g < G; g += blockDim.x) {
+      double ds = 0.0, dq = 0.0;
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { ds += (double)sb[2 * c]; dq += (double)sb[2 * c + 1]; }
+      const double mean = ds / n;
+      double var = dq / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      stats[((int64_t)b * G + g) * 2 + 0] = (float)mean;
+      stats[((int64_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+  }
+  float a[8], c[8];
+  {
+    int gprev = -1;
+    float mean = 0.f, rstd = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int ch = v * 8 + k, g = ch / cpg;
+      if (g != gprev) {
+        double ds = 0.0, dq = 0.0;
+        for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) { ds += (double)sb[2 * cc]; dq += (double)sb[2 * cc + 1]; }
+        const double m = ds / n;
+        double var = dq / n - m * m;
+        if (var < 0.0) var = 0.0;
+        mean = (float)m;
+        rstd = (float)(1.0 / sqrt(var + (double)eps));
+        gprev = g;
+      }
+      a[k] = rstd * gamma[ch];
+      c[k] = beta[ch] - mean * a[k];
+      if (apply_silu) { a[k] *= 0.5f; c[k] *= 0.5f; }
+    }
+  }
+  const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
+  const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
+  __half* yb = y + (int64_t)b * HW * ldy + v * 8;
+  for (int p = p0 + r; p < p1; p += rows * UNR) {
+    half8 hv[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) hv[u] = *reinterpret_cast<const half8*>(xb + (int64_t)(p + u * rows) * ldx);
+#pragma unroll
+    for (int u = 0; u < UNR; ++u)
+      if (p + u * rows < p1) {
+        float f[8];
+        unpack8(hv[u], f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float z = fmaf(f[k], a[k], c[k]);
+          f[k] = apply_silu ? silu_h(z) : z;
+        }
+        *reinterpret_cast<half8*>(yb + (int64_t)(p + u * rows) * ldy) = pack8(f);
+      }
+  }
+}
+
+
 // backward pass 1: per (b, split, c): s1 = sum dz, s2 = sum dz * xhat    (dz = dy * silu'(z))
 // In the loop only  z = x*a + c  (a = rstd*gamma, c = beta - mean*a) is formed; sum dz*xhat is recovered from
 // sum dz*x afterwards, so the per-thread state is 4 x 8 registers.
@@ -810,6 +883,22 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
   gn_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, st, HW, C, G, asplits, apply_silu);
   count_launch(3);
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
+int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
+                            const float* sums, int64_t ld_sums, float* stats, int B, int HW, int C, int G, float eps,
+                            int apply_silu, void* stream) {
+  BD_CHECK_ARG(x && y && gamma && beta && sums, "bd_groupnorm_apply_sums: null pointer");
+  BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && C <= 2048 && ld_sums >= 2 * (int64_t)C,
+               "bd_groupnorm_apply_sums: need C %% 8 == 0, C %% G == 0, ld %% 8 == 0, C <= 2048, ld_sums >= 2C (C=%d G=%d)", C, G);
+  if (B == 0) return BD_OK;
+  int threads, rows, splits, asplits;
+  gn_geometry(B, HW, C, 8, &threads, &rows, &splits, &asplits);
+  gn_apply_sums_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, sums, ld_sums, stats, HW, C, G, eps, asplits, apply_silu);
+  count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }

@@ -57,6 +57,8 @@ struct Conv3Params {
   int64_t ld_y;
   int out_f32;
   int* error_flag;
+  float* gn_sums;   // optional (B, ld_sums) = [channel][2]: += per-(sample, channel) sum / sum of squares of the fp16 outputs
+  int64_t ld_sums;  //   (statistics of the GroupNorm that consumes y, accumulated here so that pass never reduces)
   long long* dbg;   // optional per-CTA timeline (64 slots per CTA), bring-up only
   int epi_mode;     // bring-up: 1 = skip global stores, 2 = skip phase 2, 3 = skip the whole epilogue
 };
@@ -225,6 +227,7 @@ struct Conv3Call {
   int N; bool b_mn; bool flip;
   const float* bias; const float* bias2; const float* rowbias; int64_t ld_rowbias;
   const void* residual; int64_t ld_res; float scale; void* y; int64_t ld_y; int out_f32;
+  float* gn_sums; int64_t ld_sums;   // see Conv3Params::gn_sums (persistent / cluster kernels, fp16 stmatrix epilogue only)
 };
 
 static bool conv3_geometry(int H, int W, Conv3Params* p) {
@@ -260,6 +263,14 @@ int conv3_supported(const Conv3Call& c) {
   if (c.ld_a % 8 || (c.a2 && c.ld_a2 % 8) || c.ld_b % 8 || c.ld_y % 8 || (c.residual && c.ld_res % 8)) return 0;
   if (((uintptr_t)c.a & 15) || ((uintptr_t)c.b & 15) || (c.a2 && ((uintptr_t)c.a2 & 15))) return 0;
   return conv3_geometry(c.H, c.W, &p) ? 1 : 0;
+}
+
+// in-epilogue GroupNorm statistics: the stmatrix (fp16, residual folded into the MMA) epilogue of conv3p / conv3c only
+int conv3_gn_sums_supported(const Conv3Call& c) {
+  if (!conv3_supported(c) || c.H % 32 || c.out_f32 || c.b_mn) return 0;
+  if (getenv("BD_NO_CONV3P") || getenv("BD_NO_CONV3T") || getenv("BD_NO_GN_SUMS")) return 0;
+  if (c.residual && !(!c.a2 && c.N <= 512 && c.N % 64 == 0 && !getenv("BD_NO_RES_ID"))) return 0;   // explicit-residual epilogue
+  return 1;
 }
 
 int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensorMap& mw0, const CUtensorMap& mw1,
@@ -309,7 +320,12 @@ int conv3_launch(const Conv3Call& c_in, cudaStream_t st) {
   p.bias = c.bias; p.bias2 = c.bias2; p.rowbias = c.rowbias; p.ld_rowbias = c.ld_rowbias;
   p.residual = (const __half*)c.residual; p.ld_res = c.ld_res; p.scale = c.scale;
   p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
+  p.gn_sums = c.gn_sums; p.ld_sums = c.ld_sums;
   p.error_flag = error_flag();
+  if (c.gn_sums && !conv3_gn_sums_supported(c_in)) {
+    set_error("conv3: gn_sums needs the persistent H %% 32 == 0 kernels with fp16 output (query bd_conv_fwd_gn_sums_supported)");
+    return BD_ERR_UNSUPPORTED;
+  }
   if (wide16 && !c.residual) return conv3w_launch_fwd(c, p, st);
   {
     const char* e = getenv("BD_CONV3_DBG_PTR");  // device pointer of a (ctas x 64) int64 buffer, bring-up only
@@ -590,7 +606,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3t_kernel(const __grid_consta
 // TMEM is full with one tile (2 x 256 fp32 columns), so epilogue and MMA of consecutive tiles do not overlap; a
 // 256-pixel tile would double-buffer but doubles the weight traffic per MAC to ~41 B/clk/SM, above what L2 sustains.
 // =============================================================================================================
-template <bool A_MN>
+template <bool A_MN, bool GNS = false>   // GNS: accumulate GroupNorm statistics of the output in the stmatrix epilogue (no timeline stamps)
 __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_constant__ CUtensorMap tmX0,
                                                              const __grid_constant__ CUtensorMap tmX1,
                                                              const __grid_constant__ CUtensorMap tmW0,
@@ -681,7 +697,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
         ok = mbar_wait(tmem_empty, tph ^ 1, p.error_flag, 4);  // accumulators drained by the previous epilogue
         if (!ok) break;
         tc_fence_after();
-        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di] = clock64();   // [4i]: tile i may start
+        if (!GNS && p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di] = clock64();   // [4i]: tile i may start
         bool first = true;
         for (int seg = 0; seg < 2 && ok; ++seg) {
           const int nkb = seg ? p.nkb2 : p.nkb;
@@ -717,7 +733,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
           }
         }
         if (ok) umma_commit(tmem_full);
-        if (p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di + 1] = clock64();  // [4i+1]: last MMA of tile i issued
+        if (!GNS && p.dbg && di < 60) p.dbg[(size_t)blockIdx.x * 64 + di + 1] = clock64();  // [4i+1]: last MMA of tile i issued
         di += 4;
         tph ^= 1;
       }
@@ -743,7 +759,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
       tph ^= 1;
       if (!ok) break;
       tc_fence_after();
-      const bool stamp = p.dbg && warp == 2 && lane == 0 && di < 60;
+      const bool stamp = !GNS && p.dbg && warp == 2 && lane == 0 && di < 60;
       if (stamp) p.dbg[(size_t)blockIdx.x * 64 + di + 2] = clock64();   // [4i+2]: accumulators of tile i complete
       if (!p.out_f32 && !p.residual) {
         // ---- fp16 output: TMEM fragments -> f16x2 -> stmatrix.trans into a warp-private [16 px][32 ch] tile -> 16-byte
@@ -767,6 +783,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
         __half* ybase = reinterpret_cast<__half*>(p.y) + n_tile * C3_BN + q * 32 + (lane & 3) * 8;
         // software pipeline: the TMEM loads of chunk c+1 are in flight while chunk c goes through shared memory
         uint32_t va[8], vb[8];
+        float gs1[4] = {0.f, 0.f, 0.f, 0.f}, gs2[4] = {0.f, 0.f, 0.f, 0.f};
         {
           const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + phalf * 128;
           tmem_ld_16x256b_x2_nowait(ta, va);
@@ -780,6 +797,15 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
           for (int i = 0; i < 4; ++i) {
             m[i] = pack_f16x2((__uint_as_float(va[2 * i]) + bq[i & 1]) * sc, (__uint_as_float(va[2 * i + 1]) + bq[i & 1]) * sc);
             m[4 + i] = pack_f16x2((__uint_as_float(vb[2 * i]) + bq[2 + (i & 1)]) * sc, (__uint_as_float(vb[2 * i + 1]) + bq[2 + (i & 1)]) * sc);
+          }
+          if (GNS) {   // statistics of the ROUNDED outputs: exactly what the consumer will read back
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m[i]));
+              const int a = (i & 1) + ((i >> 2) << 1);   // channel fr + 8 a of this warp's quadrant
+              gs1[a] += f.x + f.y;
+              gs2[a] = fmaf(f.x, f.x, fmaf(f.y, f.y, gs2[a]));
+            }
           }
           if (j0 + 16 < phalf * 128 + 128) {
             const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + blk * 256 + j0 + 16;
@@ -799,6 +825,24 @@ __global__ void __launch_bounds__(576, 1) umma_conv3p_kernel(const __grid_consta
                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                          : "r"(rd_addr + it * 8 * C3P_EPI_PITCH));
             *reinterpret_cast<uint4*>(ybase + (m0 + (int64_t)it * p.W) * p.ld_y) = val;
+          }
+        }
+        if (GNS) {
+          // the 4 lanes that share a fragment row hold the same 4 channels: fold them, one lane per row issues the adds
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            gs1[a] += __shfl_xor_sync(0xffffffffu, gs1[a], 1);
+            gs1[a] += __shfl_xor_sync(0xffffffffu, gs1[a], 2);
+            gs2[a] += __shfl_xor_sync(0xffffffffu, gs2[a], 1);
+            gs2[a] += __shfl_xor_sync(0xffffffffu, gs2[a], 2);
+          }
+          if ((lane & 3) == 0) {
+            float* sp = p.gn_sums + (int64_t)n0 * p.ld_sums + 2 * (n_tile * C3_BN + q * 32 + (lane >> 2));
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              atomicAdd(sp + 16 * a, gs1[a]);
+              atomicAdd(sp + 16 * a + 1, gs2[a]);
+            }
           }
         }
       } else {
@@ -1070,6 +1114,7 @@ __global__ void __launch_bounds__(576, 1) umma_conv3c_kernel(const __grid_consta
         const float sc = p.scale;
         __half* ybase = reinterpret_cast<__half*>(p.y) + n_tile * C3_BN + q * 32 + (lane & 3) * 8;
         uint32_t va[8], vb[8];
+        float gs1[4] = {0.f, 0.f, 0.f, 0.f}, gs2[4] = {0.f, 0.f, 0.f, 0.f};
         tmem_ld_16x256b_x2_nowait(tacc + g4 * 64, va);
         tmem_ld_16x256b_x2_nowait(tacc + (16u << 16) + g4 * 64, vb);
 #pragma unroll 1
@@ -1080,6 +1125,15 @@ __global__ void __launch_bounds__(576, 1) umma_conv3c_kernel(const __grid_consta
           for (int i = 0; i < 4; ++i) {
             m[i] = pack_f16x2((__uint_as_float(va[2 * i]) + bq[i & 1]) * sc, (__uint_as_float(va[2 * i + 1]) + bq[i & 1]) * sc);
             m[4 + i] = pack_f16x2((__uint_as_float(vb[2 * i]) + bq[2 + (i & 1)]) * sc, (__uint_as_float(vb[2 * i + 1]) + bq[2 + (i & 1)]) * sc);
+          }
+          if (p.gn_sums) {   // statistics of the ROUNDED outputs: exactly what the consumer will read back
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&m[i]));
+              const int a = (i & 1) + ((i >> 2) << 1);   // channel fr + 8 a of this warp's quadrant
+              gs1[a] += f.x + f.y;
+              gs2[a] = fmaf(f.x, f.x, fmaf(f.y, f.y, gs2[a]));
+            }
           }
           if (j0 + 16 < g4 * 64 + 64) {
             tmem_ld_16x256b_x2_nowait(tacc + j0 + 16, va);
@@ -1098,6 +1152,24 @@ __global__ void __launch_bounds__(576, 1) umma_conv3c_kernel(const __grid_consta
                          : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                          : "r"(rd_addr + it * 8 * C3P_EPI_PITCH));
             *reinterpret_cast<uint4*>(ybase + (m0 + (int64_t)it * p.W) * p.ld_y) = val;
+          }
+        }
+        if (p.gn_sums) {
+          // the 4 lanes that share a fragment row hold the same 4 channels: fold them, one lane per row issues the adds
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            gs1[a] += __shfl_xor_sync(0xffffffffu, gs1[a], 1);
+            gs1[a] += __shfl_xor_sync(0xffffffffu, gs1[a], 2);
+            gs2[a] += __shfl_xor_sync(0xffffffffu, gs2[a], 1);
+            gs2[a] += __shfl_xor_sync(0xffffffffu, gs2[a], 2);
+          }
+          if ((lane & 3) == 0) {
+            float* sp = p.gn_sums + (int64_t)n0 * p.ld_sums + 2 * (n_tile * C3_BN + q * 32 + (lane >> 2));
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+              atomicAdd(sp + 16 * a, gs1[a]);
+              atomicAdd(sp + 16 * a + 1, gs2[a]);
+            }
           }
         }
       } else {
@@ -1241,8 +1313,14 @@ int conv3t_launch(const CUtensorMap& mx0, const CUtensorMap& mx1, const CUtensor
       if (!pattr[1]) { cudaFuncSetAttribute(umma_conv3p_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[1] = true; }
       launch_pdl(umma_conv3p_kernel<true>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
     } else {
-      if (!pattr[0]) { cudaFuncSetAttribute(umma_conv3p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[0] = true; }
-      launch_pdl(umma_conv3p_kernel<false>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
+      if (p.gn_sums) {
+        static bool gattr = false;
+        if (!gattr) { cudaFuncSetAttribute(umma_conv3p_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); gattr = true; }
+        launch_pdl(umma_conv3p_kernel<false, true>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
+      } else {
+        if (!pattr[0]) { cudaFuncSetAttribute(umma_conv3p_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3P_SMEM); pattr[0] = true; }
+        launch_pdl(umma_conv3p_kernel<false>, dim3(ctas), dim3(576), C3P_SMEM, st, mx0, mx1, mw0, mw1, p);
+      }
     }
     count_launch(1);
     return BD_OK;

@@ -29,10 +29,14 @@ class Act:
     backward order, whether the last writer of g was such a GroupNorm): the producer's bias gradient without a pass
     over g."""
 
-    __slots__ = ("t", "g", "g_filled", "gs", "gs_valid")
+    __slots__ = ("t", "g", "g_filled", "gs", "gs_valid", "sums", "sums_ok")
 
-    def __init__(self, t, g=None, gs=None):
+    def __init__(self, t, g=None, gs=None, sums=None):
         self.t, self.g, self.g_filled, self.gs, self.gs_valid = t, g, False, gs, False
+        # sums: (B, C, 2) fp32 view that the producing conv's epilogue fills with the per-(sample, channel) sum / sum of
+        # squares of t (forward GroupNorm statistics without a reduction pass); sums_ok: plan-time flag, every producer of
+        # t does so
+        self.sums, self.sums_ok = sums, False
 
     @property
     def C(self):
@@ -75,7 +79,16 @@ class UNetEngine:
         # two streams genuinely overlap; inside a CUDA graph the fork/join events become plain dependency edges.
         self.side = (torch.cuda.Stream(device=self.dev)
                      if train and not os.environ.get("BD_NO_SIDE_STREAM") else None)
+        # GroupNorm statistics accumulated by the producing convs (bd_conv_args.gn_sums): one arena, zeroed by ONE memset
+        # at the start of every forward; only layers at resolutions the persistent 3x3 kernels serve (H % 32 == 0) use it
+        self._sums_cap = 2 * batch * 32768 if (S % 32 == 0 and not os.environ.get("BD_NO_GN_SUMS")) else 0
+        self._sums_arena = torch.zeros(max(self._sums_cap, 1), device=self.dev)
+        self._sums_used = 0
+        self.gn_sums_layers = 0   # GroupNorms planned on the producer-statistics path (introspection / tests)
         self._build()
+        self._sums_live = self._sums_arena[: self._sums_used]
+        if self._sums_used:
+            self.fwd.insert(0, self._sums_live.zero_)
 
     # ------------------------------------------------------------------ parameter views
     def W16(self, key):
@@ -106,12 +119,35 @@ class UNetEngine:
             self._pool[key] = self.new(H, C, dtype)
         return self._pool[key]
 
+    def new_sums(self, H, C):
+        """(B, C, 2) slice of the statistics arena, or None where no producer could fill it."""
+        n = self.B * C * 2
+        if H % 32 or self._sums_used + n > self._sums_cap:
+            return None
+        v = self._sums_arena[self._sums_used: self._sums_used + n].view(self.B, C, 2)
+        self._sums_used += n
+        return v
+
     def act(self, H, C, tag="x") -> Act:
-        a = Act(self.tmp(H, C, tag))
+        a = Act(self.tmp(H, C, tag), sums=self.new_sums(H, C))
         if self.train:
             a.g = self.new(H, C)
             a.gs = torch.empty(self.B, C, device=self.dev)
         return a
+
+    def _conv3_sums(self, x_t, w, y_t, sums, residual=None, x2=None, w2=None):
+        """Plan time: `sums` if the 3x3 conv x_t -> y_t will run on a kernel whose epilogue accumulates them, else None."""
+        if sums is None:
+            return None
+        return sums if ops.conv_fwd_gn_sums_supported(x_t, w, y_t, ksize=3, residual=residual, x2=x2, w2=w2, impl=self.impl) else None
+
+    def _gn_fwd(self, x_t, y_t, gamma, beta, stats, silu, sums):
+        """GroupNorm (+SiLU) forward: streaming apply over producer-accumulated statistics when `sums` is given, else the
+        single-launch cluster kernel that reduces and applies."""
+        if sums is not None:
+            ops.groupnorm_apply_sums(x_t, y_t, gamma, beta, sums, stats, self.G, self.eps, silu)
+        else:
+            ops.groupnorm_fwd(x_t, y_t, gamma, beta, stats, self.gn_work, self.G, self.eps, silu)
 
     def _gn_bwd(self, x, dy, dx, gamma, beta, stats, dgamma, dbeta, silu, add_dx=None, gsum=None):
         """GroupNorm backward whose dgamma / dbeta leave as per-sample partials (B, 2C) and are summed over the batch by
@@ -219,12 +255,14 @@ class UNetEngine:
                 k = len(skip_specs) - 1 - n
                 assert skip_specs[k] == (sk, Hu), (skip_specs[k], sk, Hu)
                 cat = Act(self.new(Hu, ri + sk), self.new(Hu, ri + sk) if self.train else None,
-                          torch.empty(B, ri + sk, device=dev) if self.train else None)
+                          torch.empty(B, ri + sk, device=dev) if self.train else None, sums=self.new_sums(Hu, ri + sk))
                 cats.append(cat)
                 x_slots.append(Act(cat.t[..., :ri], cat.g[..., :ri] if self.train else None,
-                                   cat.gs[:, :ri] if self.train else None))
+                                   cat.gs[:, :ri] if self.train else None,
+                                   sums=cat.sums[:, :ri] if cat.sums is not None else None))
                 skip_acts[k] = Act(cat.t[..., ri:], cat.g[..., ri:] if self.train else None,
-                                   cat.gs[:, ri:] if self.train else None)
+                                   cat.gs[:, ri:] if self.train else None,
+                                   sums=cat.sums[:, ri:] if cat.sums is not None else None)
                 n += 1
             if b["up"]:
                 Hu *= 2
@@ -361,16 +399,25 @@ class UNetEngine:
         w1, b1, w2, b2 = self.W16(p + "conv1.weight"), self.P32(p + "conv1.bias"), self.W16(p + "conv2.weight"), self.P32(p + "conv2.bias")
         ws = self.W16(p + "conv_shortcut.weight") if has_sc else None
         bs = self.P32(p + "conv_shortcut.bias") if has_sc else None
-        gw = self.gn_work
+        # forward GroupNorm statistics from the producers' epilogues where every producer can deliver them
+        x_ok = all(c.sums_ok for c in cat_children) if cat_children else x.sums_ok
+        x_sums = x.sums if (x_ok and x.sums is not None) else None
+        h1_sums = self._conv3_sums(a1, w1, h1, self.new_sums(H, Cout))
+        if has_sc:
+            out_sums = self._conv3_sums(a2, w2, out.t, out.sums, x2=x.t, w2=ws)
+        else:
+            out_sums = self._conv3_sums(a2, w2, out.t, out.sums, residual=x.t)
+        out.sums_ok = out_sums is not None
+        self.gn_sums_layers += (x_sums is not None) + (h1_sums is not None)
 
         def f():
-            ops.groupnorm_fwd(x.t, a1, n1w, n1b, st1, gw, G, eps, True)
-            ops.conv_fwd(a1, w1, h1, ksize=3, bias=b1, rowbias=rowb, impl=impl)
-            ops.groupnorm_fwd(h1, a2, n2w, n2b, st2, gw, G, eps, True)
+            self._gn_fwd(x.t, a1, n1w, n1b, st1, True, x_sums)
+            ops.conv_fwd(a1, w1, h1, ksize=3, bias=b1, rowbias=rowb, impl=impl, gn_sums=h1_sums)
+            self._gn_fwd(h1, a2, n2w, n2b, st2, True, h1_sums)
             if has_sc:
-                ops.conv_fwd(a2, w2, out.t, ksize=3, bias=b2, bias2=bs, x2=x.t, w2=ws, scale=scale, impl=impl)
+                ops.conv_fwd(a2, w2, out.t, ksize=3, bias=b2, bias2=bs, x2=x.t, w2=ws, scale=scale, impl=impl, gn_sums=out_sums)
             else:
-                ops.conv_fwd(a2, w2, out.t, ksize=3, bias=b2, residual=x.t, scale=scale, impl=impl)
+                ops.conv_fwd(a2, w2, out.t, ksize=3, bias=b2, residual=x.t, scale=scale, impl=impl, gn_sums=out_sums)
 
         self.fwd.append(f)
         if not self.train:
@@ -459,8 +506,11 @@ class UNetEngine:
         wp, bp = self.W16(p + "proj_attn.weight").view(1, C, C), self.P32(p + "proj_attn.bias")
         gw = self.gn_work
 
+        x_sums = x.sums if (x.sums_ok and x.sums is not None) else None
+        self.gn_sums_layers += x_sums is not None
+
         def f():
-            ops.groupnorm_fwd(x.t, a, gnw, gnb, st, gw, G, eps, False)
+            self._gn_fwd(x.t, a, gnw, gnb, st, False, x_sums)
             ops.conv_fwd(a, wqkv, qkv, ksize=1, bias=bqkv, impl=impl)
             ops.attention_fwd(qkv.view(B, S, 3 * C), probs, ao.view(B, S, C), work, B, S, C, heads, sm_scale, impl=impl)
             ops.conv_fwd(ao, wp, out.t, ksize=1, bias=bp, residual=x.t, scale=scale, impl=impl)
@@ -537,9 +587,12 @@ class UNetEngine:
         w, b = self.W16(p + "weight"), self.P32(p + "bias")
         self.named[p] = out
 
+        out_sums = self._conv3_sums(u, w, out.t, out.sums)
+        out.sums_ok = out_sums is not None
+
         def f():
             ops.upsample2x(x.t, u)
-            ops.conv_fwd(u, w, out.t, ksize=3, bias=b, impl=impl)
+            ops.conv_fwd(u, w, out.t, ksize=3, bias=b, impl=impl, gn_sums=out_sums)
 
         self.fwd.append(f)
         if not self.train:
@@ -574,8 +627,11 @@ class UNetEngine:
         self.eps_hat = torch.empty(B, self.cfg.out_channels, H, H, device=self.dev)
         gw = self.gn_work
 
+        x_sums = x.sums if (x.sums_ok and x.sums is not None) else None
+        self.gn_sums_layers += x_sums is not None
+
         def f():
-            ops.groupnorm_fwd(x.t, a, nw, nb, st, gw, G, eps, True)
+            self._gn_fwd(x.t, a, nw, nb, st, True, x_sums)
             ops.conv_out_fwd(a, w, b, self.eps_hat)
 
         self.fwd.append(f)

@@ -130,6 +130,15 @@ def groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, silu):
                                    float(eps), int(silu), _s()))
 
 
+def groupnorm_apply_sums(x, y, gamma, beta, sums, stats, G, eps, silu):
+    """GroupNorm (+SiLU) forward from producer-accumulated channel sums (B, C, 2): one streaming launch."""
+    px, ldx, B, H, W, Cc = _view(x)
+    py, ldy, *_ = _view(y)
+    assert sums.shape[0] == B and sums.shape[1] == Cc and sums.stride(1) == 2 and sums.stride(2) == 1
+    check(L.lib().bd_groupnorm_apply_sums(px, ldx, py, ldy, _p(gamma), _p(beta), sums.data_ptr(), sums.stride(0), _p(stats),
+                                          B, H * W, Cc, G, float(eps), int(silu), _s()))
+
+
 def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None, parts=None):
     """gsum: optional (B, C) f32 view (row stride free) that receives the per-sample channel sums of dx.
     parts: optional contiguous (B, 2C) f32 that receives the per-sample {dbeta | dgamma} terms instead of the atomic
@@ -174,11 +183,28 @@ def _conv_args(x, w, y, Cin, Cout, ksize, mode, pad, bias, bias2, rowbias, resid
     return a
 
 
+def _set_gn_sums(a, gn_sums):
+    """gn_sums: (B, C, 2) f32 view (row stride free, [channel][2] contiguous) of the consumer GroupNorm's sums buffer."""
+    if gn_sums is not None:
+        assert gn_sums.dtype == torch.float32 and gn_sums.dim() == 3 and gn_sums.shape[2] == 2
+        assert gn_sums.stride(2) == 1 and gn_sums.stride(1) == 2, gn_sums.stride()
+        a.gn_sums, a.ld_sums = gn_sums.data_ptr(), gn_sums.stride(0)
+
+
 def conv_fwd(x, w, y, ksize=3, mode=L.BD_CONV_S1, pad=0, bias=None, bias2=None, rowbias=None, residual=None, x2=None,
-             w2=None, scale=1.0, impl=L.BD_IMPL_AUTO):
-    """y (B,Ho,Wo,Cout) = conv(x (B,H,W,Cin), w packed [tap][Cout][Cin]) [+ x2 @ w2] + bias + bias2 + rowbias[b] + residual."""
+             w2=None, scale=1.0, impl=L.BD_IMPL_AUTO, gn_sums=None):
+    """y (B,Ho,Wo,Cout) = conv(x (B,H,W,Cin), w packed [tap][Cout][Cin]) [+ x2 @ w2] + bias + bias2 + rowbias[b] + residual.
+    gn_sums: optional (B, Cout, 2) f32 view that receives (+=) the per-(sample, channel) sum / sum of squares of y."""
     a = _conv_args(x, w, y, x.shape[3], y.shape[3], ksize, mode, pad, bias, bias2, rowbias, residual, x2, w2, scale, impl)
+    _set_gn_sums(a, gn_sums)
     check(L.lib().bd_conv_fwd(C.byref(a), _s()))
+
+
+def conv_fwd_gn_sums_supported(x, w, y, ksize=3, mode=L.BD_CONV_S1, pad=0, residual=None, x2=None, w2=None,
+                               impl=L.BD_IMPL_AUTO) -> bool:
+    """Plan-time query: would this bd_conv_fwd run on a kernel whose epilogue can accumulate gn_sums?"""
+    a = _conv_args(x, w, y, x.shape[3], y.shape[3], ksize, mode, pad, None, None, None, residual, x2, w2, 1.0, impl)
+    return bool(L.lib().bd_conv_fwd_gn_sums_supported(C.byref(a)))
 
 
 def conv_dgrad(dy, w, dx, ksize=3, mode=L.BD_CONV_S1, pad=0, residual=None, scale=1.0, impl=L.BD_IMPL_AUTO):

@@ -138,6 +138,12 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
                      float* stats, float* work, int B, int HW, int C, int G, float eps, int apply_silu, void* stream);
 /* backward: dx = GN'(dy (* SiLU')) [+ add_dx]; dgamma / dbeta f32 are ACCUMULATED into (zero them first).
  * work: bd_gn_workspace_floats(B, C) floats.                                                          */
+/* GroupNorm (+SiLU) forward as a pure streaming pass over statistics that the producing conv accumulated (`sums`, see
+ * bd_conv_args.gn_sums; channel c of x at sums[b*ld_sums + 2c]): D/models/resnet.py:553-559,588-591 without the
+ * reduction pass.  stats (B,G,2) = {mean, rstd} out (nullable), as bd_groupnorm_fwd writes them for the backward. */
+int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
+                            const float* sums, int64_t ld_sums, float* stats, int B, int HW, int C, int G, float eps,
+                            int apply_silu, void* stream);
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
                      float* dbeta, float* dgb_work,
@@ -181,9 +187,17 @@ typedef struct bd_conv_args {
   float out_scale;                  /* multiplies the result (1/output_scale_factor)          */
   void* y; int64_t ld_y; int out_dtype;     /* BD_OUT_F16 / BD_OUT_F32 NHWC view             */
   int impl;                         /* BD_IMPL_*                                             */
+  /* GroupNorm statistics of the OUTPUT accumulated in the epilogue (bd_conv_fwd only, nullable): gn_sums[b*ld_sums +
+   * 2*c + {0,1}] += sum / sum of squares over the pixels of sample b of the fp16-rounded outputs of channel c (c counts
+   * from this call's first output channel; for a channel slice of a wider tensor pass the slice's address).  The caller
+   * zeroes the buffer; bd_groupnorm_apply_sums consumes it.  Only where bd_conv_fwd_gn_sums_supported() says so. */
+  float* gn_sums; int64_t ld_sums;
 } bd_conv_args;
 
 int bd_conv_fwd(const bd_conv_args* a, void* stream);
+/* 1 if bd_conv_fwd would run `a` on a kernel whose epilogue can accumulate gn_sums (the persistent / cluster 3x3
+ * tcgen05 kernels: stride 1, H %% 32 == 0, fp16 output), else 0.  Plan-time query, launches nothing. */
+int bd_conv_fwd_gn_sums_supported(const bd_conv_args* a);
 /* dgrad: dx (B,H,W,Cin) = conv^T(dy (B,Ho,Wo,Cout)) with the SAME packed forward weight (read as an
  * MN-major operand).  `residual` is added (gradient fan-in), x2/w2 unused.  Uses the same struct:
  * x:=dy, y:=dx, Cin/Cout keep their FORWARD meaning.                                                    */

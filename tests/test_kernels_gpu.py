@@ -704,3 +704,47 @@ def test_pndm_step_bit_exact(ops, golden):
                 step += 1
             assert torch.equal(x.cpu(), T(g[f"{tag}/out"][k - 1])), tag
     assert n == 56
+
+
+@pytest.mark.parametrize("B,H,Cin,Cout,res", [(3, 32, 128, 128, False), (2, 32, 64, 256, True), (5, 64, 128, 128, False)])
+def test_conv_epilogue_gn_sums_and_apply(ops, B, H, Cin, Cout, res):
+    """GroupNorm fusion, step one (resnet.py:553-559,588-591): the 3x3 conv's epilogue accumulates the per-(sample, channel)
+    sum / sum of squares of its fp16 outputs, bd_groupnorm_apply_sums is a pure streaming pass over them.
+    (a) the conv output is bitwise the one without gn_sums; (b) the sums equal those of the stored output (fp32 atomics:
+    1e-5 relative); (c) y and the saved (mean, rstd) match the reducing GroupNorm kernel on the same input (2e-3 / 1e-5)."""
+    torch.manual_seed(1)
+    G, eps = 32, 1e-6
+    x = torch.randn(B, H, H, Cin, device="cuda").half()
+    w = (torch.randn(9, Cout, Cin, device="cuda") / (3 * Cin ** 0.5)).half()
+    bias, rowb = torch.randn(Cout, device="cuda"), torch.randn(B, Cout, device="cuda")
+    r = torch.randn(B, H, H, Cout, device="cuda").half() if res else None
+    y0 = torch.empty(B, H, H, Cout, dtype=torch.half, device="cuda")
+    ops.conv_fwd(x, w, y0, ksize=3, bias=bias, rowbias=rowb, residual=r, scale=0.5 if res else 1.0)
+    assert ops.conv_fwd_gn_sums_supported(x, w, y0, ksize=3, residual=r)
+    assert not ops.conv_fwd_gn_sums_supported(x[:, :16, :16], w, y0[:, :16, :16], ksize=3)
+    # sums live in a slice of a wider (concat) statistics buffer: row stride 2 * (Cout + 64)
+    wide = torch.zeros(B, Cout + 64, 2, device="cuda")
+    sums = wide[:, 64:]
+    for variant in ("0", None):   # persistent kernel, then whatever the round-fill heuristic picks (cluster kernel at 64x64)
+        if variant is None:
+            os.environ.pop("BD_CONV3C", None)
+        else:
+            os.environ["BD_CONV3C"] = variant
+        wide.zero_()
+        y = torch.empty_like(y0)
+        ops.conv_fwd(x, w, y, ksize=3, bias=bias, rowbias=rowb, residual=r, scale=0.5 if res else 1.0, gn_sums=sums)
+        assert ops.umma_error() == 0 and torch.equal(y, y0)
+        yf = y.float().reshape(B, H * H, Cout)
+        ref = torch.stack([yf.sum(1), (yf * yf).sum(1)], dim=-1)
+        assert float((sums - ref).abs().max()) <= 1e-5 * float(ref.abs().max()), float((sums - ref).abs().max())
+        assert float(wide[:, :64].abs().max()) == 0.0
+    os.environ.pop("BD_CONV3C", None)
+    gamma, beta = torch.randn(Cout, device="cuda") * 0.2 + 1, torch.randn(Cout, device="cuda") * 0.2
+    for silu in (True, False):
+        a_ref, a = torch.empty_like(y), torch.empty_like(y)
+        st_ref, st = torch.empty(B, G, 2, device="cuda"), torch.empty(B, G, 2, device="cuda")
+        work = torch.empty(ops.gn_workspace_floats(B, Cout), device="cuda")
+        ops.groupnorm_fwd(y, a_ref, gamma, beta, st_ref, work, G, eps, silu)
+        ops.groupnorm_apply_sums(y, a, gamma, beta, sums, st, G, eps, silu)
+        assert float((st - st_ref).abs().max()) <= 1e-5 * max(1.0, float(st_ref.abs().max()))
+        assert float((a.float() - a_ref.float()).abs().max()) <= 2e-3 * max(1.0, float(a_ref.float().abs().max()))
