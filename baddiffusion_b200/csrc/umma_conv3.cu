@@ -267,9 +267,10 @@ int conv3_supported(const Conv3Call& c) {
 
 // in-epilogue GroupNorm statistics: the stmatrix (fp16, residual folded into the MMA) epilogue of conv3p / conv3c only
 int conv3_gn_sums_supported(const Conv3Call& c) {
-  if (!conv3_supported(c) || c.H % 32 || c.out_f32 || c.b_mn) return 0;
-  if (getenv("BD_NO_CONV3P") || getenv("BD_NO_CONV3T") || getenv("BD_NO_GN_SUMS")) return 0;
+  if (!conv3_supported(c) || c.out_f32 || c.b_mn || getenv("BD_NO_GN_SUMS")) return 0;
   if (c.residual && !(!c.a2 && c.N <= 512 && c.N % 64 == 0 && !getenv("BD_NO_RES_ID"))) return 0;   // explicit-residual epilogue
+  if (c.H == 16 && c.W == 16 && c.N % 256 == 0 && !getenv("BD_NO_CONV3W")) return 1;                 // conv3w: one image per CTA
+  if (c.H % 32 || getenv("BD_NO_CONV3P") || getenv("BD_NO_CONV3T")) return 0;
   return 1;
 }
 
@@ -1536,12 +1537,22 @@ __global__ void __launch_bounds__(576, 1) umma_conv3w_kernel(const __grid_consta
           stmatrix_x4(base + 32, m[4], m[5], m[6], m[7]);   // channels +16..31
         }
         __syncwarp();
+        float gs1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, gs2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int it = 0; it < 4; ++it) {                  // 8 pixels (one image row of the block) x 64 bytes per step
           uint4 val;
           asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
                        : "r"(rd_addr + it * 8 * C3W_EPI_PITCH));
+          if (p.gn_sums) {   // GroupNorm statistics of the rounded outputs: this lane = 8 channels of one pixel
+            const __half2* h = reinterpret_cast<const __half2*>(&val);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float2 f = __half22float2(h[k]);
+              gs1[2 * k] += f.x; gs1[2 * k + 1] += f.y;
+              gs2[2 * k] = fmaf(f.x, f.x, gs2[2 * k]); gs2[2 * k + 1] = fmaf(f.y, f.y, gs2[2 * k + 1]);
+            }
+          }
           if (!p.out_f32) {
             *reinterpret_cast<uint4*>(ybase + (int64_t)it * p.W * p.ld_y + c0) = val;
           } else {
@@ -1550,6 +1561,24 @@ __global__ void __launch_bounds__(576, 1) umma_conv3w_kernel(const __grid_consta
             const float2 f0 = __half22float2(h[0]), f1 = __half22float2(h[1]), f2 = __half22float2(h[2]), f3 = __half22float2(h[3]);
             *reinterpret_cast<float4*>(yr) = make_float4(f0.x, f0.y, f1.x, f1.y);
             *reinterpret_cast<float4*>(yr + 4) = make_float4(f2.x, f2.y, f3.x, f3.y);
+          }
+        }
+        if (p.gn_sums) {   // fold the 8 lanes (pixels) that hold the same 8 channels, lanes 0..3 issue the adds
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+#pragma unroll
+            for (int o = 4; o < 32; o <<= 1) {
+              gs1[k] += __shfl_xor_sync(0xffffffffu, gs1[k], o);
+              gs2[k] += __shfl_xor_sync(0xffffffffu, gs2[k], o);
+            }
+          }
+          if (lane < 4) {
+            float* sp = p.gn_sums + (int64_t)n0 * p.ld_sums + 2 * (n_tile * C3W_BN + col + lane * 8);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              atomicAdd(sp + 2 * k, gs1[k]);
+              atomicAdd(sp + 2 * k + 1, gs2[k]);
+            }
           }
         }
       }

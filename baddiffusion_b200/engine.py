@@ -80,7 +80,7 @@ class UNetEngine:
         self.side = (torch.cuda.Stream(device=self.dev)
                      if train and not os.environ.get("BD_NO_SIDE_STREAM") else None)
         # GroupNorm statistics accumulated by the producing convs (bd_conv_args.gn_sums): one arena, zeroed by ONE memset
-        # at the start of every forward; only layers at resolutions the persistent 3x3 kernels serve (H % 32 == 0) use it
+        # at the start of every forward; only layers at resolutions the halo-reuse 3x3 kernels serve (H % 32 == 0, 16 x 16) use it
         self._sums_cap = 2 * batch * 32768 if (S % 32 == 0 and not os.environ.get("BD_NO_GN_SUMS")) else 0
         self._sums_arena = torch.zeros(max(self._sums_cap, 1), device=self.dev)
         self._sums_used = 0
@@ -122,7 +122,7 @@ class UNetEngine:
     def new_sums(self, H, C):
         """(B, C, 2) slice of the statistics arena, or None where no producer could fill it."""
         n = self.B * C * 2
-        if H % 32 or self._sums_used + n > self._sums_cap:
+        if (H % 32 and H != 16) or self._sums_used + n > self._sums_cap:
             return None
         v = self._sums_arena[self._sums_used: self._sums_used + n].view(self.B, C, 2)
         self._sums_used += n
