@@ -197,14 +197,14 @@ def test_pipelines_match_reference(golden):
                        output_type=None).images
             ref = g[f"ddpm_{vt}_{int(clip)}_25"]
             print(f"ddpm {vt} clip={clip}: max {np.abs(out - ref).max():.3e} mean {np.abs(out - ref).mean():.3e}")
-            assert out.shape == ref.shape and np.abs(out - ref).mean() < 2e-2
+            assert out.shape == ref.shape and np.abs(out - ref).mean() < 7e-4      # measured 1.2e-4 .. 1.4e-4
     sched = DDPMScheduler(variance_type="fixed_large", clip_sample=True)
     pipe = DDPMPipeline(unet=m, scheduler=sched)
     pipe.set_progress_bar_config(disable=True)
     res = pipe(batch_size=3, generator=torch.Generator().manual_seed(9), num_inference_steps=10, output_type=None,
                save_every_step=True)
     print(f"ddpm fresh 10: mean {np.abs(res.images - g['ddpm_fresh_10']).mean():.3e}")
-    assert np.abs(res.images - g["ddpm_fresh_10"]).mean() < 5e-3
+    assert np.abs(res.images - g["ddpm_fresh_10"]).mean() < 6e-4      # measured 1.2e-4
     mov = np.stack(res.movie)
     assert mov.shape == g["ddpm_fresh_10_movie"].shape
     assert np.array_equal(mov[0], g["ddpm_fresh_10_movie"][0])  # step 0 is the init itself: bit exact
@@ -212,12 +212,14 @@ def test_pipelines_match_reference(golden):
     out = batch_sampling(6, lambda **kw: pipe(num_inference_steps=20, **kw), init=init, max_batch_n=4,
                          rng=torch.Generator().manual_seed(13))
     print(f"batch_sampling 6 by 4 (20 steps): mean {np.abs(out - g['batch_sampling_6_by_4']).mean():.3e}")
-    assert out.shape == (6, 32, 32, 3) and np.abs(out - g["batch_sampling_6_by_4"]).mean() < 2e-2
+    assert out.shape == (6, 32, 32, 3) and np.abs(out - g["batch_sampling_6_by_4"]).mean() < 6e-4      # measured 1.2e-4
     dpipe = DDIMPipeline(unet=m, scheduler=sched)
     dpipe.set_progress_bar_config(disable=True)
     out = dpipe(batch_size=6, num_inference_steps=8, init=init, output_type=None).images
     print(f"ddim 8: max {np.abs(out - g['ddim_8']).max():.3e} mean {np.abs(out - g['ddim_8']).mean():.3e}")
-    # eta=0 chains have no noise injection to damp the ~2x/step amplification of the fp16 operand error
+    # eta=0 chains have no noise injection to damp the ~2x/step amplification of the fp16 operand error on the random-init
+    # UNet (measured mean 8.7e-3 here, 4.3e-2 for the 10-step backdoor chain below; the fp32 oracle shows the same growth
+    # under a 1e-3 input perturbation): per-step parity of these samplers is pinned teacher-forced below
     assert np.abs(out - g["ddim_8"]).mean() < 3e-2
     out = dpipe(batch_size=6, num_inference_steps=10, init=bd_init, output_type=None).images
     print(f"ddim 10 backdoor: max {np.abs(out - g['ddim_10_backdoor']).max():.3e} mean {np.abs(out - g['ddim_10_backdoor']).mean():.3e}")
@@ -225,11 +227,11 @@ def test_pipelines_match_reference(golden):
     out = dpipe(batch_size=6, num_inference_steps=10, init=init, eta=1.0, generator=torch.Generator().manual_seed(21),
                 output_type=None).images
     print(f"ddim 10 eta=1: max {np.abs(out - g['ddim_10_eta1']).max():.3e} mean {np.abs(out - g['ddim_10_eta1']).mean():.3e}")
-    assert np.abs(out - g["ddim_10_eta1"]).mean() < 6e-2
+    assert np.abs(out - g["ddim_10_eta1"]).mean() < 2e-3      # measured 3.4e-4 (noise injection damps the amplification)
     out = pipe(batch_size=6, generator=torch.Generator().manual_seed(3), num_inference_steps=25, init=bd_init,
                output_type=None).images
     print(f"ddpm backdoor 25: mean {np.abs(out - g['ddpm_backdoor_25']).mean():.3e}")
-    assert np.abs(out - g["ddpm_backdoor_25"]).mean() < 2e-2
+    assert np.abs(out - g["ddpm_backdoor_25"]).mean() < 6e-4      # measured 1.2e-4
     pil = dpipe(batch_size=2, num_inference_steps=2, output_type="pil").images
     assert len(pil) == 2 and pil[0].size == (32, 32)
 
@@ -250,7 +252,7 @@ def test_ddpm_1000_step_chain_matches_reference(golden):
     ref = g["ddpm_nogen_init_1000"]
     d = np.abs(out - ref)
     print(f"ddpm 1000 steps: max {d.max():.3e} mean {d.mean():.3e} (ref mean {ref.mean():.3f} std {ref.std():.3f})")
-    assert out.shape == ref.shape and d.mean() < 5e-2
+    assert out.shape == ref.shape and d.mean() < 6e-4 and d.max() < 8e-3      # measured mean 1.1e-4, max 1.5e-3
 
 
 def test_teacher_forced_sampling_steps(golden):
@@ -338,5 +340,5 @@ def test_pndm_pipeline_matches_reference(golden):
         ref = g[f"pipe_clip{int(clip)}_20/images"]
         err = np.abs(res.images - ref)
         print(f"pndm 20 clip={clip}: max {err.max():.3e} mean {err.mean():.3e}")
-        assert res.images.shape == ref.shape and len(res.movie) == 30 and err.mean() < 3e-2
-        assert np.abs(np.stack(res.movie[-3:]) - g[f"pipe_clip{int(clip)}_20/movie_last3"]).mean() < 3e-2
+        assert res.images.shape == ref.shape and len(res.movie) == 30 and err.mean() < 2e-3      # measured 7e-5 / 3e-4
+        assert np.abs(np.stack(res.movie[-3:]) - g[f"pipe_clip{int(clip)}_20/movie_last3"]).mean() < 2e-3
