@@ -99,7 +99,15 @@ __global__ void gn_finalize_kernel(const float* __restrict__ work, float* __rest
   const int b = blockIdx.x;
   for (int g = threadIdx.x; g < G; g += blockDim.x) {
     double ds = 0.0, dq = 0.0;
-    for (int sp = 0; sp < splits; ++sp) {
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {   // 8 independent loads in flight per sum (same fixed order of the adds)
+      float2 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float2*>(work + (((int64_t)b * splits + sp + u) * G + g) * 2);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { ds += (double)w[u].x; dq += (double)w[u].y; }
+    }
+    for (; sp < splits; ++sp) {
       const float* w = work + (((int64_t)b * splits + sp) * G + g) * 2;
       ds += (double)w[0];
       dq += (double)w[1];
@@ -311,12 +319,24 @@ __global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restri
   extern __shared__ float cs[];
   const int b = blockIdx.x, cpg = C / G;
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    float s1 = 0.f, s2 = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float* w = work + (((int64_t)b * splits + sp) * 2) * C;
-      s1 += w[c];
-      s2 += w[C + c];
+    // 8 loads per sum in flight: with few samples (CelebA-HQ: B = 4 -> 4 CTAs) the split count is ~100 and a single
+    // dependent chain of L2 round trips made this tiny kernel 24 us; the summation order stays fixed
+    float a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* w0 = work + ((int64_t)b * splits * 2) * C + c;
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a1[u] += w0[(int64_t)(sp + u) * 2 * C];
+        a2[u] += w0[(int64_t)(sp + u) * 2 * C + C];
+      }
     }
+    for (; sp < splits; ++sp) {
+      a1[0] += w0[(int64_t)sp * 2 * C];
+      a2[0] += w0[(int64_t)sp * 2 * C + C];
+    }
+    const float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+    const float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
     cs[c] = s1;
     cs[C + c] = s2;
     if (dgb_parts) {
@@ -342,14 +362,18 @@ __global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restri
 
 // backward pass 2:  dx = rstd*(dz*gamma - gA - xhat*gB) (+ add)  ==  k1*dz + c1*x + c0 (+ add)  with per-channel
 // k1 = rstd*gamma, c1 = -rstd^2*gB, c0 = rstd*(mean*rstd*gB - gA);  z = x*k1 + cz for the SiLU derivative.
-__global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
+template <bool GSUM>
+__global__ void __launch_bounds__(256, GSUM ? 2 : 3) gn_bwd_apply_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
     const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-    const float* __restrict__ gab, int HW, int C, int G, int asplits, int apply_silu) {
+    const float* __restrict__ gab, int HW, int C, int G, int asplits, int apply_silu, float* __restrict__ gsum,
+    int64_t ld_gsum) {
+  extern __shared__ float gsred[];   // [rows][C] when gsum is requested
   const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   float k1[8], cz[8], c1[8], c0[8];
+  float gs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // channel sums of this thread's (rounded) dx rows
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = v * 8 + k, g = ch / cpg;
@@ -380,7 +404,26 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_apply_kernel(
         if (add) o += fa[k];
         fx[k] = o;
       }
-      *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = pack8(fx);
+      const half8 hv = pack8(fx);
+      *reinterpret_cast<half8*>(dx + row * lddx + v * 8) = hv;
+      if (GSUM) {
+        float fr[8];
+        unpack8(hv, fr);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) gs[k] += fr[k];
+      }
+    }
+  }
+  if (GSUM) {
+    // per-sample channel sums of dx (the producer's bias gradient / the temb gradient) without a second pass over dx:
+    // block-level fold through shared memory, one atomic per (CTA, channel) into the zeroed (B, C) view
+#pragma unroll
+    for (int k = 0; k < 8; ++k) gsred[r * C + v * 8 + k] = gs[k];
+    __syncthreads();
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+      float t = 0.f;
+      for (int rr = 0; rr < rows; ++rr) t += gsred[rr * C + c];
+      atomicAdd(gsum + (int64_t)b * ld_gsum + c, t);
     }
   }
 }
@@ -937,15 +980,17 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
   // group sums live right behind the per-split partials in the workspace
   float* gab = work + (size_t)B * splits * 2 * C;
   gn_bwd_group_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(work, gamma, gab, dgamma, dbeta, dgb_parts, HW, C, G, splits);
-  gn_bwd_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
-      stats, gab, HW, C, G, asplits, apply_silu);
+  if (gsum) cudaMemset2DAsync(gsum, (size_t)ld_gsum * sizeof(float), 0, (size_t)C * sizeof(float), B, (cudaStream_t)stream);
+  if (gsum)
+    gn_bwd_apply_kernel<true><<<dim3(asplits, B), threads, (size_t)rows * C * sizeof(float), (cudaStream_t)stream>>>(
+        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
+        stats, gab, HW, C, G, asplits, apply_silu, gsum, ld_gsum);
+  else
+    gn_bwd_apply_kernel<false><<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
+        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
+        stats, gab, HW, C, G, asplits, apply_silu, nullptr, 0);
   count_launch(3);
   BD_CHECK_LAUNCH();
-  if (gsum) {
-    cudaMemset2DAsync(gsum, (size_t)ld_gsum * sizeof(float), 0, (size_t)C * sizeof(float), B, (cudaStream_t)stream);
-    return bd_colsum_f16(dx, ld_dx, gsum, ld_gsum, B, HW, C, 1, stream);
-  }
   return BD_OK;
 }
 

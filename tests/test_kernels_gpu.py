@@ -722,7 +722,7 @@ def test_conv_epilogue_gn_sums_and_apply(ops, B, H, Cin, Cout, res):
     y0 = torch.empty(B, H, H, Cout, dtype=torch.half, device="cuda")
     ops.conv_fwd(x, w, y0, ksize=3, bias=bias, rowbias=rowb, residual=r, scale=0.5 if res else 1.0)
     assert ops.conv_fwd_gn_sums_supported(x, w, y0, ksize=3, residual=r)
-    assert not ops.conv_fwd_gn_sums_supported(x[:, :8, :8], w, y0[:, :8, :8], ksize=3)      # 8x8: generic one-tile kernel
+    assert not ops.conv_fwd_gn_sums_supported(x[:, :8, :8].contiguous(), w, y0[:, :8, :8].contiguous(), ksize=3)   # 8x8: generic one-tile kernel
     # sums live in a slice of a wider (concat) statistics buffer: row stride 2 * (Cout + 64)
     wide = torch.zeros(B, Cout + 64, 2, device="cuda")
     sums = wide[:, 64:]
