@@ -313,8 +313,10 @@ def test_checkpoint_layout_roundtrip(tmp_path):
     assert isinstance(pipe, DDPMPipeline)
     _, sched2, gp2 = DiffuserModelSched.get_pretrained(d, noise_sched_type="DDIM-SCHED")
     assert type(sched2).__name__ == "DDIMScheduler"
+    _, sched3, gp3 = DiffuserModelSched.get_pretrained(d, noise_sched_type="UNIPC-SCHED")     # model.py:616-618 -> PNDMPipeline
+    assert type(sched3).__name__ == "PNDMScheduler" and type(gp3(unet, sched3)).__name__ == "PNDMPipeline"
     with pytest.raises(NotImplementedError):
-        DiffuserModelSched.get_pretrained(d, noise_sched_type="UNIPC-SCHED")
+        DiffuserModelSched.get_pretrained(d, noise_sched_type="SCORE-SDE-VE-SCHED")
     with pytest.raises(EnvironmentError):
         DiffuserModelSched.get_pretrained("DDPM-CIFAR10-32")  # hub id, no network
 
