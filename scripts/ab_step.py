@@ -12,12 +12,14 @@ from baddiffusion_b200.train import Trainer
 from baddiffusion_b200.unet import UNet2DModel
 
 variants = sys.argv[1:] or [""]
-B, K = 128, 10
+ARCH = os.environ.get("AB_ARCH", "DDPM-CIFAR10-32")            # AB_ARCH=DDPM-CELEBA-HQ-256 AB_BATCH=4: BASELINE configs[3]
+B, K = int(os.environ.get("AB_BATCH", "128")), 10
 _lib.lib()
 torch.manual_seed(0)
-model = UNet2DModel(**DiffuserModelSched.ARCH["DDPM-CIFAR10-32"]).cuda()
+model = UNet2DModel(**DiffuserModelSched.ARCH[ARCH]).cuda()
 sched = DDPMScheduler(variance_type="fixed_large")
-ds = SyntheticDataset(32, 3, poison_rate=0.1)
+ds = (SyntheticDataset(256, 3, poison_rate=0.1, trigger="GLASSES", target="CAT") if "256" in ARCH
+      else SyntheticDataset(32, 3, poison_rate=0.1))
 hb = ds.batch(B)
 KEYS = set()
 for v in variants:

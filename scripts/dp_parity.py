@@ -42,6 +42,7 @@ def run(pg, lo, hi, overlap):
     os.environ["BD_NO_AR_OVERLAP"] = "0" if overlap else "1"
     torch.manual_seed(0)
     model = UNet2DModel(**DiffuserModelSched.ARCH["DDPM-CIFAR10-32"]).cuda()
+    p_init = model.flat_params.clone()
     tr = Trainer(model, DDPMScheduler(variance_type="fixed_large"), hi - lo, trig, targ, lr=2e-4, total_steps=100, warmup_steps=1,
                  process_group=pg, seed=1)
     losses, grads = [], []
@@ -50,14 +51,14 @@ def run(pg, lo, hi, overlap):
         torch.cuda.synchronize()
         grads.append(tr.gflat.clone() / tr.loss_scale)
     assert _lib.lib().bd_umma_error() == 0
-    return model.flat_params.clone(), grads, losses
+    return model.flat_params.clone(), grads, losses, p_init
 
 
 verdict = {}
 lo, hi = shard_for_rank(GB, rank, world)
 res = {mode: run(dist.group.WORLD, lo, hi, mode == "overlap") for mode in ("overlap", "single")}
 ref = run(None, 0, GB, False) if rank == 0 else None
-for mode, (params, grads, losses) in res.items():
+for mode, (params, grads, losses, _) in res.items():
     lt = torch.tensor(losses, device="cuda", dtype=torch.float64)
     dist.all_reduce(lt)
     lt /= world
@@ -65,12 +66,15 @@ for mode, (params, grads, losses) in res.items():
     allc = [torch.zeros_like(chk) for _ in range(world)]
     dist.all_gather(allc, chk)
     if rank == 0:
-        rp, rg, rl = ref
+        rp, rg, rl, p0 = ref
         cos = min(float((a @ b) / (a.norm() * b.norm())) for a, b in zip(grads, rg))
         nrel = max(abs(float(a.norm()) - float(b.norm())) / float(b.norm()) for a, b in zip(grads, rg))
         verdict[mode] = {"grad_cos": cos, "grad_norm_rel": nrel,
                          "loss_rel": max(abs(float(a) - b) / abs(b) for a, b in zip(lt, rl)),
                          "param_max_abs": float((params - rp).abs().max()),
+                         # Adam moves every element by ~lr whatever its gradient's size: elements whose gradient is within
+                         # fp16 noise of zero may flip sign (max-abs up to 2 lr per step), so compare the UPDATE in the 2-norm
+                         "param_update_rel": float((params - rp).norm() / (rp - p0).norm()),
                          "replicas_equal": all(float(c) == float(allc[0]) for c in allc)}
 if rank == 0:
     print(json.dumps(verdict), flush=True)
