@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(256, 4) gn_apply_kernel(const __half* __restri
 // no cluster barrier, any number of CTAs per sample.  Every thread derives (mean, rstd) of the groups its 8 channels
 // belong to from the channel sums (<= 2 * C/G floats per group, L2-resident, fp64 combine); block (0, b) also writes
 // stats (B, G, 2) for the backward.  Same affine-then-silu_h arithmetic as gn_apply_kernel.
+constexpr int GN_APPLY_MAXG = 256;
 __global__ void __launch_bounds__(256, 4) gn_apply_sums_kernel(const __half* __restrict__ x, int64_t ldx,
                                                                __half* __restrict__ y, int64_t ldy,
                                                                const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -176,39 +177,36 @@ __global__ void __launch_bounds__(256, 4) gn_apply_sums_kernel(const __half* __r
   const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const float* sb = sums + (int64_t)b * ld_sums;
+  // (mean, rstd) of every group ONCE per CTA (G threads, fp64 combine), then broadcast through shared memory: doing the
+  // fp64 divide / sqrt in every thread made this pass a flat 24 us whatever its size (ncu: xu 42 %, dram 17 %)
+  __shared__ float sm_mean[GN_APPLY_MAXG], sm_rstd[GN_APPLY_MAXG];
   const double n = (double)HW * cpg;
-  if (blockIdx.x == 0 && stats) {
-    for (int g = threadIdx.x; g < G; g += blockDim.x) {
-      double ds = 0.0, dq = 0.0;
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) { ds += (double)sb[2 * c]; dq += (double)sb[2 * c + 1]; }
-      const double mean = ds / n;
-      double var = dq / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      stats[((int64_t)b * G + g) * 2 + 0] = (float)mean;
-      stats[((int64_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      const float2 sq = *reinterpret_cast<const float2*>(sb + 2 * c);
+      ds += (double)sq.x;
+      dq += (double)sq.y;
+    }
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float m = (float)mean, rs = (float)(1.0 / sqrt(var + (double)eps));
+    sm_mean[g] = m;
+    sm_rstd[g] = rs;
+    if (blockIdx.x == 0 && stats) {
+      stats[((int64_t)b * G + g) * 2 + 0] = m;
+      stats[((int64_t)b * G + g) * 2 + 1] = rs;
     }
   }
+  __syncthreads();
   float a[8], c[8];
-  {
-    int gprev = -1;
-    float mean = 0.f, rstd = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int ch = v * 8 + k, g = ch / cpg;
-      if (g != gprev) {
-        double ds = 0.0, dq = 0.0;
-        for (int cc = g * cpg; cc < (g + 1) * cpg; ++cc) { ds += (double)sb[2 * cc]; dq += (double)sb[2 * cc + 1]; }
-        const double m = ds / n;
-        double var = dq / n - m * m;
-        if (var < 0.0) var = 0.0;
-        mean = (float)m;
-        rstd = (float)(1.0 / sqrt(var + (double)eps));
-        gprev = g;
-      }
-      a[k] = rstd * gamma[ch];
-      c[k] = beta[ch] - mean * a[k];
-      if (apply_silu) { a[k] *= 0.5f; c[k] *= 0.5f; }
-    }
+  for (int k = 0; k < 8; ++k) {
+    const int ch = v * 8 + k, g = ch / cpg;
+    a[k] = sm_rstd[g] * gamma[ch];
+    c[k] = beta[ch] - sm_mean[g] * a[k];
+    if (apply_silu) { a[k] *= 0.5f; c[k] *= 0.5f; }
   }
   const int p0 = (int)((int64_t)HW * blockIdx.x / asplits), p1 = (int)((int64_t)HW * (blockIdx.x + 1) / asplits);
   const __half* xb = x + (int64_t)b * HW * ldx + v * 8;
@@ -936,6 +934,7 @@ int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, 
   BD_CHECK_ARG(x && y && gamma && beta && sums, "bd_groupnorm_apply_sums: null pointer");
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_y % 8 == 0 && C <= 2048 && ld_sums >= 2 * (int64_t)C,
                "bd_groupnorm_apply_sums: need C %% 8 == 0, C %% G == 0, ld %% 8 == 0, C <= 2048, ld_sums >= 2C (C=%d G=%d)", C, G);
+  BD_CHECK_ARG(G <= GN_APPLY_MAXG, "bd_groupnorm_apply_sums: at most %d groups", GN_APPLY_MAXG);
   if (B == 0) return BD_OK;
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 8, &threads, &rows, &splits, &asplits);

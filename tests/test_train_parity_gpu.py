@@ -200,7 +200,7 @@ def test_two_rank_nccl_gradient_matches_global_batch(tmp_path):
         assert v[mode]["grad_cos"] >= 0.9999 and v[mode]["grad_norm_rel"] <= 2e-3, v
         assert v[mode]["loss_rel"] <= 1e-4 and v[mode]["replicas_equal"], v
         # two steps, the first at lr 0 (warm-up), the second at 2e-4: a sign flip of a noise-level gradient moves 2 lr
-        assert v[mode]["param_update_rel"] <= 5e-2 and v[mode]["param_max_abs"] <= 4.5e-4, v
+        assert v[mode]["param_update_rel"] <= 2.5e-2 and v[mode]["param_max_abs"] <= 4.5e-4, v
 
 
 def test_trainer_u8_input_equals_fp32_input():
