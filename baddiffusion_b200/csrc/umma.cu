@@ -34,6 +34,8 @@ struct FpropParams {
   KSeg seg[kMaxSeg];
   int total_kblocks;
   int splits;            // split-K factor = cluster size along z (1: none)
+  int mshare;            // CTAs of a cluster along x (neighbouring M tiles of one N tile) that SHARE every B (weight) tile:
+                         // each fetches 1/mshare of it and TMA-multicasts the slice into all of them (1: none)
   int tiles_w, tiles_h;  // tiles per image
   int bw, bh, bn;        // pixel box (product 128)
   int W, H, NB;          // image geometry
@@ -90,7 +92,7 @@ struct Smem {
 // fprop-style kernel
 // =============================================================================================
 template <int BN, int kStages, bool B_MN>
-__global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
+__global__ void __launch_bounds__(320, BN == 256 ? 1 : 2) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                             const __grid_constant__ CUtensorMap tmA1,
                                                             const __grid_constant__ CUtensorMap tmB0,
                                                             const __grid_constant__ CUtensorMap tmB1,
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
     prefetch_tmap(&tmB1);
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], p.mshare);   // a stage is refilled only when every CTA that receives its B slices has consumed it
     }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
@@ -124,12 +126,17 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
   if (warp == 1) tmem_alloc(tmem_slot, BN);
   tc_fence_before();
   __syncthreads();
+  if (p.mshare > 1) cluster_sync_all();   // every CTA's barriers exist before a peer multicasts into them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_launch_dependents();
   pdl_wait();   // prologue above overlaps the previous kernel; global memory is touched only below
-  // split-K: rank r of the (1,1,S) cluster owns k-blocks [it_begin, it_end) of the flattened segment list
-  const int S = p.splits, rank = S > 1 ? (int)cluster_ctarank() : 0;
+  // cluster (CM, 1, S): rank = x + CM * z.  split-K: split index z owns k-blocks [it_begin, it_end) of the flattened
+  // segment list; the CM CTAs with the same z walk the same k-blocks in lockstep and share the B tiles
+  const int S = p.splits, CM = p.mshare;
+  const int crank = (S > 1 || CM > 1) ? (int)cluster_ctarank() : 0;
+  const int rank = crank / CM, mrank = crank - rank * CM;
+  const uint16_t share_mask = (uint16_t)(((1u << CM) - 1u) << (rank * CM));
   const int it_begin = (int)((long long)p.total_kblocks * rank / S), it_end = (int)((long long)p.total_kblocks * (rank + 1) / S);
 
   if (warp == 0) {
@@ -151,12 +158,25 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
           mbar_expect_tx(&full[stage], L::kStageBytes);
           tma_load_4d(mapA, &full[stage], sa, sg.a_c0 + kb * BK, w0 * p.a_stride + sg.dx - p.dbg_shift, h0 * p.a_stride + sg.dy, n0);
           const int bz = sg.b_z + (p.batched ? n0 : 0);
-          if (!B_MN) {
-            tma_load_3d(mapB, &full[stage], sb, sg.b_k0 + kb * BK, n_tile * BN, bz);
+          if (CM == 1) {
+            if (!B_MN) {
+              tma_load_3d(mapB, &full[stage], sb, sg.b_k0 + kb * BK, n_tile * BN, bz);
+            } else {
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                tma_load_3d(mapB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, sg.b_k0 + kb * BK, bz);
+            }
+          } else if (!B_MN) {
+            // this CTA's BN/CM rows of the K-major tile, into the same slot of every CTA that shares it
+            const int rows = BN / CM;
+            tma_load_3d_mc(mapB, &full[stage], sb + mrank * rows * 128, sg.b_k0 + kb * BK, n_tile * BN + mrank * rows, bz, share_mask);
           } else {
+            // MN-major tile = BN/64 slabs of [64 k][64 n]: this CTA's 64/CM k-rows of every slab
+            const int krows = 64 / CM;
 #pragma unroll
             for (int i = 0; i < BN / 64; ++i)
-              tma_load_3d(mapB, &full[stage], sb + i * (64 * BK * 2), n_tile * BN + i * 64, sg.b_k0 + kb * BK, bz);
+              tma_load_3d_mc(mapB, &full[stage], sb + i * (64 * BK * 2) + mrank * krows * 128, n_tile * BN + i * 64,
+                             sg.b_k0 + kb * BK + mrank * krows, bz, share_mask);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -181,7 +201,8 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
           const uint64_t bd = make_desc(sb + (B_MN ? k * 2048 : k * 32), p.b_lbo, p.b_sbo);
           umma_f16(tmem_base, ad, bd, p.idesc, (it > it_begin || k > 0) ? 1u : 0u);
         }
-        umma_commit(&empty[stage]);  // frees the smem stage when these MMAs retire
+        // frees the smem stage when these MMAs retire -- in every CTA that multicasts into it
+        if (CM == 1) umma_commit(&empty[stage]); else umma_commit_mc(&empty[stage], share_mask);
         if (++stage == kStages) { stage = 0; phase ^= 1; }
       }
       if (ok) umma_commit(tmem_full);
@@ -208,12 +229,14 @@ __global__ void __launch_bounds__(320, 2) umma_fprop_kernel(const __grid_constan
       if (ok) epilogue_stage_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane);
       cluster_sync_all();   // every rank's partial tile is staged (all threads of the cluster take part, see below)
       epilogue_splitk_finish_warp<BN / 2>(stage, lane, S, rank, m, mlin, valid, n_tile * BN + half * (BN / 2), e, p.rowbias,
-                                          p.ld_rowbias, p.HW);
+                                          p.ld_rowbias, p.HW, CM, mrank);
     }
   }
   if (S > 1) {
     if (warp < 2) cluster_sync_all();   // producer / MMA warps: the barrier the epilogue warps passed after staging
     cluster_sync_all();                 // no CTA retires while a peer still reads its staging tile
+  } else if (CM > 1) {
+    cluster_sync_all();                 // ... or still multicasts into its ring / arrives on its barriers
   }
   tc_fence_before();
   __syncthreads();
@@ -612,7 +635,7 @@ static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
     attr_set = true;
   }
-  if (p.splits > 1) {
+  if (p.splits > 1 || p.mshare > 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = dim3(320);
@@ -620,14 +643,15 @@ static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CU
     cfg.stream = st;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 1;
+    attr[0].val.clusterDim.x = p.mshare;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = p.splits;
     attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = getenv("BD_NO_PDL") ? 1 : 2;
-    cudaLaunchKernelEx(&cfg, kern, a0, a1, b, b1, p);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, a0, a1, b, b1, p);
+    if (e != cudaSuccess) { set_error("umma fprop: cluster launch (%d,1,%d) failed: %s", p.mshare, p.splits, cudaGetErrorString(e)); return BD_ERR_CUDA; }
   } else {
     launch_pdl(kern, grid, dim3(320), (size_t)L::kTotal, st, a0, a1, b, b1, p);
   }
@@ -677,7 +701,21 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   p.HW = c.HW_rowbias > 0 ? c.HW_rowbias : c.H * c.W;
   p.N = c.N;
   p.batched = c.batched ? 1 : 0;
-  const int BN = (c.N % 128 == 0) ? 128 : 64;
+  // BN = 256 (one CTA computes both 128-channel halves of a 256-multiple layer from ONE fetch of its A tiles) for the
+  // few-tile, long-K launches (the 3x3 convolutions at 8x8 / 4x4): OFF by default.  The idea was that the per-tap A
+  // re-fetch makes those launches L2->SM bound; measured inside the train step (scripts/ab_step.py, profiles/
+  // r2_ab_step_mshare.log) it LOSES 0.57 ms/step -- half as many, twice as fat CTAs (192 KB of shared memory, one per SM)
+  // no longer share SMs with the weight-gradient kernels of the side stream, and the launches are latency- not
+  // bandwidth-bound.  BD_BN256=1 enables it for experiments.
+  int BN = (c.N % 128 == 0) ? 128 : 64;
+  {
+    int bw, bh, bn;
+    pick_box(c.H, c.W, BM, &bw, &bh, &bn);
+    const long long mt = (long long)(c.W / bw) * (c.H / bh) * ceil_div(c.NB, bn);
+    const int taps0 = c.ntap_override > 0 ? c.ntap_override : c.ks * c.ks;
+    const int kblocks0 = taps0 * (c.Ca / 64) + (c.a2 ? c.Ca2 / 64 : 0);
+    if (c.N % 256 == 0 && !c.batched && kblocks0 >= 18 && mt * (c.N / 128) <= num_sms() && getenv("BD_BN256")) BN = 256;
+  }
   // K segments
   int nseg = 0, total = 0;
   const int taps = c.ntap_override > 0 ? c.ntap_override : c.ks * c.ks;
@@ -738,20 +776,6 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   } else {
     ma1 = ma0;
   }
-  {
-    uint64_t dims[3] = {(uint64_t)c.b_cols, (uint64_t)c.b_rows, (uint64_t)c.b_z};
-    uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
-    uint32_t box[3] = {64, c.b_mn ? 64u : (uint32_t)BN, 1};
-    if (!make_map(&mb, c.b, 3, dims, str, box)) return BD_ERR_CUDA;
-  }
-  if (c.a2) {
-    uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
-    uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
-    uint32_t box[3] = {64, (uint32_t)BN, 1};
-    if (!make_map(&mb1, c.b2, 3, dims, str, box)) return BD_ERR_CUDA;
-  } else {
-    mb1 = mb;
-  }
   const int m_tiles = p.tiles_w * p.tiles_h * ceil_div(c.NB, p.bn);
   // split-K (cluster of S CTAs per output tile) when the tile grid leaves most SMs idle and K is long: the 3x3 convs
   // of the 8x8 / 4x4 levels (128 / 32 tiles, 36-72 k-blocks each)
@@ -759,11 +783,42 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   if (!getenv("BD_NO_SPLITK")) {
     const int tiles = m_tiles * (c.N / BN);
     const int budget = (int)env_u32("BD_SPLITK_CTAS", num_sms());   // stay at one CTA per SM: the 6-stage ring below
-    while (p.splits < 4 && tiles * p.splits * 2 <= budget && p.total_kblocks / (p.splits * 2) >= 6) p.splits *= 2;
+    const int max_splits = (int)env_u32("BD_SPLITK_MAX", BN == 256 ? 8 : 4), min_kb = BN == 256 ? 4 : 6;
+    while (p.splits < max_splits && tiles * p.splits * 2 <= budget && p.total_kblocks / (p.splits * 2) >= min_kb) p.splits *= 2;
+  }
+  // B-tile sharing: in the few-tile, long-K regime the weight tiles are the larger half of the L2->SM traffic and every M
+  // tile of an N tile reads the same ones.  The `mshare` CTAs of a cluster along x fetch 1/mshare of each B tile and
+  // multicast it (cluster = (mshare, 1, splits) <= 8 CTAs).  Correct (tests/test_kernels_gpu.py bench-sized cases run it
+  // with BD_FPROP_MSHARE=4) but OFF by default: inside the train step it costs +0.4 ms (clusters of 8 one-CTA-per-SM
+  // blocks wait for 8 free SMs of one GPC while the side stream's kernels hold some, and the sharing CTAs move in
+  // lockstep).  BD_FPROP_MSHARE=2|4 enables it.
+  p.mshare = 1;
+  {
+    const long long ctas = (long long)m_tiles * (c.N / BN) * p.splits;
+    const int want = (int)env_u32("BD_FPROP_MSHARE", 1);
+    if (!c.batched && c.ks == 3 && ctas <= num_sms() && p.total_kblocks / p.splits >= 4 && p.dbg_shift == 0) {
+      int cm = want;
+      while (cm > 1 && (m_tiles % cm || cm * p.splits > 8 || (c.b_mn ? 64 % cm : BN % cm))) cm >>= 1;
+      p.mshare = cm < 1 ? 1 : cm;
+    }
+  }
+  {
+    uint64_t dims[3] = {(uint64_t)c.b_cols, (uint64_t)c.b_rows, (uint64_t)c.b_z};
+    uint64_t str[2] = {(uint64_t)c.ld_b, (uint64_t)c.b_rows * c.ld_b};
+    uint32_t box[3] = {64, (c.b_mn ? 64u : (uint32_t)BN) / (uint32_t)p.mshare, 1};   // mshare > 1: the slice one CTA multicasts
+    if (!make_map(&mb, c.b, 3, dims, str, box)) return BD_ERR_CUDA;
+  }
+  if (c.a2) {
+    uint64_t dims[3] = {(uint64_t)c.Ca2, (uint64_t)c.N, 1};
+    uint64_t str[2] = {(uint64_t)c.ld_b2, (uint64_t)c.N * c.ld_b2};
+    uint32_t box[3] = {64, (uint32_t)BN / (uint32_t)p.mshare, 1};
+    if (!make_map(&mb1, c.b2, 3, dims, str, box)) return BD_ERR_CUDA;
+  } else {
+    mb1 = mb;
   }
   dim3 grid(m_tiles, c.N / BN, p.splits);
   // many small-K tiles: persistent kernel (one CTA per SM, double-buffered TMEM)
-  if (BN == 128 && p.splits == 1 && (long long)m_tiles * (c.N / BN) > 2 * num_sms() && p.total_kblocks <= 16 && p.dbg_shift == 0 &&
+  if (BN == 128 && p.splits == 1 && p.mshare == 1 && (long long)m_tiles * (c.N / BN) > 2 * num_sms() && p.total_kblocks <= 16 && p.dbg_shift == 0 &&
       !getenv("BD_NO_FPROP_PERSIST")) {
     constexpr int kSt = 4;
     using LP = SmemP<128, kSt>;
@@ -781,7 +836,9 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
     return BD_OK;
   }
   const bool deep = (long long)grid.x * grid.y * grid.z <= num_sms() && p.total_kblocks / p.splits >= 6 && !getenv("BD_NO_DEEP_RING");
-  if (BN == 128) {
+  if (BN == 256) {
+    if (c.b_mn) launch_fprop_t<256, true, 4>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<256, false, 4>(ma0, ma1, mb, mb1, p, grid, st);
+  } else if (BN == 128) {
     if (deep) {
       if (c.b_mn) launch_fprop_t<128, true, 6>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<128, false, 6>(ma0, ma1, mb, mb1, p, grid, st);
     } else {

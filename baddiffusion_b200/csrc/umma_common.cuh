@@ -311,7 +311,7 @@ template <int CW>
 __device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restrict__ stage, int lane, int S, int rank,
                                                             int64_t m_own, int64_t mlin_own, bool valid_own, int col0,
                                                             const EpiArgs& e, const float* __restrict__ rowbias,
-                                                            int64_t ld_rowbias, int HW) {
+                                                            int64_t ld_rowbias, int HW, int rank_stride = 1, int rank_off = 0) {
   constexpr int PITCH = CW + 4;
   constexpr int LPR = CW / 8;
   constexpr int RPI = 32 / LPR;
@@ -335,7 +335,9 @@ __device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restr
     const uint32_t sp = smem_u32(stage + row * PITCH + piece * 8);
     float f[8] = {bsum[0], bsum[1], bsum[2], bsum[3], bsum[4], bsum[5], bsum[6], bsum[7]};
     for (int rk = 0; rk < S; ++rk) {
-      const float4 a = ld_dsmem_f4(sp, rk), b = ld_dsmem_f4(sp + 16, rk);
+      // split index rk lives in cluster rank rank_off + rank_stride * rk (clusters that also share B tiles along x)
+      const uint32_t cr = (uint32_t)(rank_off + rank_stride * rk);
+      const float4 a = ld_dsmem_f4(sp, cr), b = ld_dsmem_f4(sp + 16, cr);
       f[0] += a.x; f[1] += a.y; f[2] += a.z; f[3] += a.w; f[4] += b.x; f[5] += b.y; f[6] += b.z; f[7] += b.w;
     }
     if (rowbias) {

@@ -331,11 +331,20 @@ def test_conv_wgrad(ops, impl, B, H, Cin, Cout, k):
                                           (9, 16, 128, 512),    # two 256-channel slabs; dgrad falls back (N = 128)
                                           (128, 4, 256, 256),   # split-K cluster of 4 (32 tiles)
                                           (128, 8, 512, 256)])  # split-K cluster of 2 (128 tiles), 72 k-blocks
-def test_conv3_bench_sized_kernels(ops, B, H, Cin, Cout):
+@pytest.mark.parametrize("variant", ["default", "mshare4", "bn256_mshare4"])
+def test_conv3_bench_sized_kernels(ops, monkeypatch, variant, B, H, Cin, Cout):
     """The persistent 32x32 kernel (conv3p), the 256-wide 16x16 kernel (conv3w) and the split-K cluster path of the
     generic kernel at the bench's per-GPU sizes: forward (bias + per-sample row bias + residual through the identity
     K-segment + scale), the fused 1x1 shortcut segment, dgrad, all against torch fp32 on the same fp16 inputs."""
     im = ops.L.BD_IMPL_UMMA
+    # off-by-default variants of the generic kernel (measured slower inside the step, kept correct): weight tiles
+    # multicast across the M tiles of a cluster (BD_FPROP_MSHARE) and 256-wide N tiles with split-K up to 8 (BD_BN256)
+    if variant != "default":
+        if H > 8:
+            pytest.skip("variants of the generic one-tile kernel only (8x8 / 4x4 layers)")
+        monkeypatch.setenv("BD_FPROP_MSHARE", "4")
+        if variant == "bn256_mshare4":
+            monkeypatch.setenv("BD_BN256", "1")
     x, xr, w, wr = _conv_inputs(B, H, Cin, Cout, 3, seed=3)
     bias = torch.randn(Cout, device="cuda")
     rowbias = torch.randn(B, Cout, device="cuda")
