@@ -589,13 +589,21 @@ bool make_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, c
   return true;
 }
 
-static int* g_error_flag = nullptr;  // device int, lazily allocated once per process (not per call)
+// one device int PER DEVICE, lazily allocated on first use there (not per call): a process that drives several GPUs
+// (nn.DataParallel-style callers) gets a valid flag on each
+static int* g_error_flag[64] = {nullptr};
+static int current_device_slot() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev < 0 || dev >= 64) ? 0 : dev;
+}
 int* error_flag() {
-  if (!g_error_flag) {
-    cudaMalloc(&g_error_flag, sizeof(int));
-    cudaMemset(g_error_flag, 0, sizeof(int));
+  const int d = current_device_slot();
+  if (!g_error_flag[d]) {
+    cudaMalloc(&g_error_flag[d], sizeof(int));
+    cudaMemset(g_error_flag[d], 0, sizeof(int));
   }
-  return g_error_flag;
+  return g_error_flag[d];
 }
 
 uint32_t env_u32(const char* name, uint32_t dflt) {
@@ -948,9 +956,10 @@ int wgrad_launch(const WgradCall& c, cudaStream_t st) {
 
 int read_error_flag() {
   int v = 0;
-  if (g_error_flag) {
-    cudaMemcpy(&v, g_error_flag, sizeof(int), cudaMemcpyDeviceToHost);
-    if (v) cudaMemset(g_error_flag, 0, sizeof(int));
+  int* f = g_error_flag[current_device_slot()];
+  if (f) {
+    cudaMemcpy(&v, f, sizeof(int), cudaMemcpyDeviceToHost);
+    if (v) cudaMemset(f, 0, sizeof(int));
   }
   return v;
 }
