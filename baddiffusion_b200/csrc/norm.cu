@@ -174,6 +174,8 @@ __global__ void __launch_bounds__(256, 4) gn_apply_sums_kernel(const __half* __r
                                                                const float* __restrict__ sums, int64_t ld_sums,
                                                                float* __restrict__ stats, int HW, int C, int G, float eps,
                                                                int asplits, int apply_silu) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
   const int b = blockIdx.y, cpg = C / G, C8 = C / 8, rows = blockDim.x / C8;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const float* sb = sums + (int64_t)b * ld_sums;
@@ -938,8 +940,21 @@ int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, 
   if (B == 0) return BD_OK;
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 8, &threads, &rows, &splits, &asplits);
-  gn_apply_sums_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, sums, ld_sums, stats, HW, C, G, eps, asplits, apply_silu);
+  {
+    // programmatic dependent launch like the cluster kernels: the CTAs are scheduled while the producing conv drains
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(asplits, B);
+    cfg.blockDim = dim3(threads);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = getenv("BD_NO_PDL") ? 0 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, gn_apply_sums_kernel, (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, sums,
+                                       ld_sums, stats, HW, C, G, eps, asplits, apply_silu);
+    if (e != cudaSuccess) { set_error("bd_groupnorm_apply_sums: launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+  }
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
