@@ -370,3 +370,78 @@ def test_groupnorm_statistics_plan(monkeypatch):
     err = float(((a - b) ** 2).mean())
     print(f"eps_hat MSE, producer statistics vs reducing GroupNorm kernels: {err:.3e}")
     assert err <= 1.5e-6
+
+
+def test_every_layer_of_the_cifar_unet_teacher_forced():
+    """Layer-level parity (the reference pins these layers one by one in T/models/test_layers_utils.py,
+    the oracle's layer functions are pinned to those fixtures on the CPU): run the CUDA plan once, then for EVERY ResnetBlock2D,
+    AttentionBlock (256-token fused kernel and the 16-token mid block), Downsample2D and Upsample2D of the CIFAR10 UNet feed
+    the plan's own input activation of that layer to the fp32 oracle layer and compare outputs -- no error accumulates
+    across layers, so each kernel composition is judged alone.  Bound: 2.5e-3 of the layer's max |output| (fp16 operands:
+    2^-11 per rounding, K up to 9*512 products per output)."""
+    from oracle import torch_ref as O
+
+    cfg = O.CIFAR10_CONFIG
+    m, sd = _model(cfg)
+    B = 3
+    x = torch.randn(B, 3, 32, 32, generator=torch.Generator().manual_seed(1)).cuda()
+    t = torch.tensor([3, 400, 999]).cuda()
+    eng = m.engine(B, True)          # training plan: every activation keeps its own storage
+    eng.forward(x, t)
+    torch.cuda.synchronize()
+    emb = eng.emb.float().cpu()
+    g, eps, hd = cfg["norm_num_groups"], cfg["norm_eps"], cfg["attention_head_dim"]
+    nchw = lambda a: a.t.float().permute(0, 3, 1, 2).cpu()
+    topo = O.unet_topology(cfg)
+    worst, checked = 0.0, 0
+
+    def check(name, got, ref):
+        nonlocal worst, checked
+        e = float((got - ref).abs().max() / ref.abs().max())
+        worst, checked = max(worst, e), checked + 1
+        assert e <= 2.5e-3, (name, e)      # measured worst 4.8e-4
+
+    cur = nchw(eng.named["conv_in."])
+    skips = [cur]
+    for i, b in enumerate(topo["down"]):
+        for j in range(len(b["resnets"])):
+            p = f"down_blocks.{i}.resnets.{j}."
+            out = nchw(eng.named[p])
+            check(p, out, O.resnet_block(sd, p, cur, emb, g, eps))
+            cur = out
+            if b["attn"]:
+                p = f"down_blocks.{i}.attentions.{j}."
+                out = nchw(eng.named[p])
+                check(p, out, O.attention_block(sd, p, cur, g, eps, hd))
+                cur = out
+            skips.append(cur)
+        if b["down"]:
+            p = f"down_blocks.{i}.downsamplers.0."
+            out = nchw(eng.named[p + "conv."])
+            check(p, out, O.downsample(sd, p, cur, cfg["downsample_padding"]))
+            cur = out
+            skips.append(cur)
+    for p, fn in (("mid_block.resnets.0.", "r"), ("mid_block.attentions.0.", "a"), ("mid_block.resnets.1.", "r")):
+        out = nchw(eng.named[p])
+        ref = O.resnet_block(sd, p, cur, emb, g, eps) if fn == "r" else O.attention_block(sd, p, cur, g, eps, hd)
+        check(p, out, ref)
+        cur = out
+    for i, b in enumerate(topo["up"]):
+        for j in range(len(b["resnets"])):
+            cat = torch.cat([cur, skips.pop()], dim=1)
+            p = f"up_blocks.{i}.resnets.{j}."
+            out = nchw(eng.named[p])
+            check(p, out, O.resnet_block(sd, p, cat, emb, g, eps))
+            cur = out
+            if b["attn"]:
+                p = f"up_blocks.{i}.attentions.{j}."
+                out = nchw(eng.named[p])
+                check(p, out, O.attention_block(sd, p, cur, g, eps, hd))
+                cur = out
+        if b["up"]:
+            p = f"up_blocks.{i}.upsamplers.0."
+            out = nchw(eng.named[p + "conv."])
+            check(p, out, O.upsample(sd, p, cur))
+            cur = out
+    print(f"{checked} layers, worst relative max error {worst:.3e}")
+    assert checked == 22 + 6 + 3 + 3
