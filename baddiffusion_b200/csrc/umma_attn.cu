@@ -47,6 +47,111 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// Row op of one 128-row block: thread = query row r (TMEM lane), column half h of the S_-wide score row held in TMEM at
+// `tsc` (this thread's lane, first column of the block's scores).  MODE 0: P = softmax(scale S); MODE 1: dS = scale P (dP -
+// rowsum(dP P)) with P re-read from the saved probabilities.  The fp16 result goes to shared memory in the UMMA K-major
+// SWIZZLE_128B layout (element (r, key j) at  smem_p + (j / 64) * 16 KB + r * 128 + (((j % 64) / 8) ^ (r & 7)) * 16 +
+// (j % 8) * 2) and to global.  xch: float[2][2][128] exchange of the row max / sum (or delta) between the two halves;
+// both `bar.sync 1, 256` are executed by all 256 row-op threads.
+template <int S_, int MODE>
+__device__ __forceinline__ void attn_row_op(uint32_t tsc, uint8_t* smem_p, float* xch, int r, int h, int64_t grow,
+                                            const AttnParams& p) {
+  constexpr int NC = S_ / 2;
+  float* xm = xch + h * 128 + r;
+  float* xs = xch + 256 + h * 128 + r;
+  const float* xm_o = xch + (h ^ 1) * 128 + r;
+  __half* prow_out = p.p_out + grow * S_ + h * NC;
+  uint8_t* prow_s = smem_p + r * 128;
+  const uint32_t trow = tsc - h * NC;   // the code below adds h * NC itself
+  if (MODE == 0) {
+    uint32_t raw[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c += 32) tmem_ld32_nowait(trow + h * NC + c, raw + c);
+    tmem_wait_ld();
+    float v[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(raw[j]);
+    float m = v[0];
+#pragma unroll
+    for (int j = 1; j < NC; ++j) m = fmaxf(m, v[j]);
+    *xm = m;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    m = fmaxf(m, *xm_o);
+    const float sc = p.scale * 1.4426950408889634f;
+    const float ms = m * sc;
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      v[j] = ex2_approx(fmaf(v[j], sc, -ms));
+      sum += v[j];
+    }
+    *xs = sum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float inv = 1.0f / (xch[256 + r] + xch[256 + 128 + r]);   // same association in both halves
+#pragma unroll
+    for (int j = 0; j < NC; j += 8) {
+      uint4 u;
+      u.x = pack_f16x2(v[j] * inv, v[j + 1] * inv);
+      u.y = pack_f16x2(v[j + 2] * inv, v[j + 3] * inv);
+      u.z = pack_f16x2(v[j + 4] * inv, v[j + 5] * inv);
+      u.w = pack_f16x2(v[j + 6] * inv, v[j + 7] * inv);
+      const int key = h * NC + j;
+      *reinterpret_cast<uint4*>(prow_s + (key >> 6) * 16384 + ((((key & 63) >> 3) ^ (r & 7)) << 4)) = u;
+      *reinterpret_cast<uint4*>(prow_out + j) = u;
+    }
+  } else {
+    const __half* prow_in = p.probs_in + grow * S_ + h * NC;
+    float dsum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < NC; c += 32) {
+      uint32_t v[32];
+      tmem_ld32_nowait(trow + h * NC + c, v);
+      uint4 pu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pu[i] = *reinterpret_cast<const uint4*>(prow_in + c + i * 8);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&pu[i]);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hp[k]);
+          dsum = fmaf(f.x, __uint_as_float(v[i * 8 + 2 * k]), dsum);
+          dsum = fmaf(f.y, __uint_as_float(v[i * 8 + 2 * k + 1]), dsum);
+        }
+      }
+    }
+    *xm = dsum;
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    const float delta = xch[r] + xch[128 + r];
+#pragma unroll 1
+    for (int c = 0; c < NC; c += 32) {
+      uint32_t v[32];
+      tmem_ld32_nowait(trow + h * NC + c, v);
+      uint4 pu[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) pu[i] = *reinterpret_cast<const uint4*>(prow_in + c + i * 8);
+      tmem_wait_ld();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __half2* hp = reinterpret_cast<const __half2*>(&pu[i]);
+        float d[8];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = __half22float2(hp[k]);
+          d[2 * k] = f.x * (__uint_as_float(v[i * 8 + 2 * k]) - delta) * p.scale;
+          d[2 * k + 1] = f.y * (__uint_as_float(v[i * 8 + 2 * k + 1]) - delta) * p.scale;
+        }
+        uint4 u;
+        u.x = pack_f16x2(d[0], d[1]); u.y = pack_f16x2(d[2], d[3]); u.z = pack_f16x2(d[4], d[5]); u.w = pack_f16x2(d[6], d[7]);
+        const int key = h * NC + c + i * 8;
+        *reinterpret_cast<uint4*>(prow_s + (key >> 6) * 16384 + ((((key & 63) >> 3) ^ (r & 7)) << 4)) = u;
+        *reinterpret_cast<uint4*>(prow_out + c + i * 8) = u;
+      }
+    }
+  }
+}
+
 // S_ = keys per image (128 or 256), CW = C / 2 (epilogue column window per warp), MODE 0 = forward, 1 = backward (dQ)
 template <int S_, int CW, int MODE>
 __global__ void __launch_bounds__(320, 1) umma_attn_kernel(const __grid_constant__ CUtensorMap tmA,
@@ -154,104 +259,11 @@ __global__ void __launch_bounds__(320, 1) umma_attn_kernel(const __grid_constant
     const int q = warp & 3, h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-    float* xm = xch + h * 128 + r;            // quantity 0 (max / delta), this half
-    float* xs = xch + 256 + h * 128 + r;      // quantity 1 (sum)
-    const float* xm_o = xch + (h ^ 1) * 128 + r;
-    const float* xs_o = xch + 256 + (h ^ 1) * 128 + r;
     const int64_t grow = (int64_t)row0 + r;   // global row in (B*S)
-    __half* prow_out = p.p_out + grow * S_ + h * NC;
-    // P element (row r, key j) lives at  smem_p + (j / 64) * 16 KB + r * 128 + (((j % 64) / 8) ^ (r & 7)) * 16 + (j % 8) * 2
-    uint8_t* prow_s = smem_p + r * 128;
     bool ok = mbar_wait(s_full, 0, p.error_flag, 14);
     tc_fence_after();
     if (ok) {
-      if (MODE == 0) {
-        uint32_t raw[NC];
-#pragma unroll
-        for (int c = 0; c < NC; c += 32) tmem_ld32_nowait(trow + h * NC + c, raw + c);
-        tmem_wait_ld();
-        float v[NC];
-#pragma unroll
-        for (int j = 0; j < NC; ++j) v[j] = __uint_as_float(raw[j]);
-        float m = v[0];
-#pragma unroll
-        for (int j = 1; j < NC; ++j) m = fmaxf(m, v[j]);
-        *xm = m;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        m = fmaxf(m, *xm_o);
-        const float sc = p.scale * 1.4426950408889634f;
-        const float ms = m * sc;
-        float sum = 0.f;
-#pragma unroll
-        for (int j = 0; j < NC; ++j) {
-          v[j] = ex2_approx(fmaf(v[j], sc, -ms));
-          sum += v[j];
-        }
-        *xs = sum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float inv = 1.0f / (xch[256 + r] + xch[256 + 128 + r]);   // same association in both halves
-#pragma unroll
-        for (int j = 0; j < NC; j += 8) {
-          uint4 u;
-          u.x = pack_f16x2(v[j] * inv, v[j + 1] * inv);
-          u.y = pack_f16x2(v[j + 2] * inv, v[j + 3] * inv);
-          u.z = pack_f16x2(v[j + 4] * inv, v[j + 5] * inv);
-          u.w = pack_f16x2(v[j + 6] * inv, v[j + 7] * inv);
-          const int key = h * NC + j;
-          *reinterpret_cast<uint4*>(prow_s + (key >> 6) * 16384 + ((((key & 63) >> 3) ^ (r & 7)) << 4)) = u;
-          *reinterpret_cast<uint4*>(prow_out + j) = u;
-        }
-      } else {
-        const __half* prow_in = p.probs_in + grow * S_ + h * NC;
-        float dsum = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < NC; c += 32) {
-          uint32_t v[32];
-          tmem_ld32_nowait(trow + h * NC + c, v);
-          uint4 pu[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pu[i] = *reinterpret_cast<const uint4*>(prow_in + c + i * 8);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half2* hp = reinterpret_cast<const __half2*>(&pu[i]);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __half22float2(hp[k]);
-              dsum = fmaf(f.x, __uint_as_float(v[i * 8 + 2 * k]), dsum);
-              dsum = fmaf(f.y, __uint_as_float(v[i * 8 + 2 * k + 1]), dsum);
-            }
-          }
-        }
-        *xm = dsum;
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        const float delta = xch[r] + xch[128 + r];
-#pragma unroll 1
-        for (int c = 0; c < NC; c += 32) {
-          uint32_t v[32];
-          tmem_ld32_nowait(trow + h * NC + c, v);
-          uint4 pu[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pu[i] = *reinterpret_cast<const uint4*>(prow_in + c + i * 8);
-          tmem_wait_ld();
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const __half2* hp = reinterpret_cast<const __half2*>(&pu[i]);
-            float d[8];
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float2 f = __half22float2(hp[k]);
-              d[2 * k] = f.x * (__uint_as_float(v[i * 8 + 2 * k]) - delta) * p.scale;
-              d[2 * k + 1] = f.y * (__uint_as_float(v[i * 8 + 2 * k + 1]) - delta) * p.scale;
-            }
-            uint4 u;
-            u.x = pack_f16x2(d[0], d[1]); u.y = pack_f16x2(d[2], d[3]); u.z = pack_f16x2(d[4], d[5]); u.w = pack_f16x2(d[6], d[7]);
-            const int key = h * NC + c + i * 8;
-            *reinterpret_cast<uint4*>(prow_s + (key >> 6) * 16384 + ((((key & 63) >> 3) ^ (r & 7)) << 4)) = u;
-            *reinterpret_cast<uint4*>(prow_out + c + i * 8) = u;
-          }
-        }
-      }
+      attn_row_op<S_, MODE>(trow + h * NC, smem_p, xch, r, h, grow, p);
       fence_proxy_async();    // generic-proxy writes of the P tile -> visible to the tensor core's async-proxy reads
       tc_fence_before();
       __syncwarp();
@@ -272,6 +284,187 @@ __global__ void __launch_bounds__(320, 1) umma_attn_kernel(const __grid_constant
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
+}
+
+// =============================================================================================================
+// Per-image variant for S = 256 ("attn2", the default): ONE CTA owns BOTH 128-query blocks of an image.
+//   * K / V cross L2 -> SM once per image instead of once per query block: a phase-1 ring entry holds the k-block of Q_A,
+//     Q_B and K (64 KB) and feeds two MMAs chains (S_A in TMEM columns 0..255, S_B in 256..511); a phase-2 entry holds one
+//     64-key block of V and feeds O_A and O_B;
+//   * the output accumulators REUSE the score columns (O_A over S_A, O_B over S_B): the row op has consumed the scores
+//     before p_ready lets the first P V MMA write there, so 2 x (256 + 0) = 512 columns serve both blocks;
+//   * 128 CTAs for B = 128 = one wave on 148 SMs (the one-tile kernel ran 256 CTAs in two waves, every CTA a serial chain
+//     load -> QK^T -> row op -> PV -> epilogue of ~23 kcycles with nothing to overlap it).
+// Shared memory (192 KB): three 64 KB regions R0 | R1 | R2.  Phase 1: a 3-entry operand ring.  After the last score MMA
+// retires R1 / R2 become P_A / P_B (written by the row op in the UMMA K-major layout) and R0 the 2-entry V ring; after
+// the last P V MMA everything is epilogue staging.
+// =============================================================================================================
+constexpr int A2_REGION = 64 * 1024;
+constexpr int A2_XCH_OFFSET = 3 * A2_REGION;
+constexpr int A2_BAR_OFFSET = A2_XCH_OFFSET + 2 * 2 * 128 * 4;
+constexpr int A2_SMEM = A2_BAR_OFFSET + (3 + 3 + 1 + 2 + 2 + 2 + 1) * 8 + 16 + 1024;
+static_assert(A2_SMEM <= 232448, "attention (per-image) shared memory");
+
+template <int CW, int MODE>
+__global__ void __launch_bounds__(320, 1) umma_attn2_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                            const __grid_constant__ CUtensorMap tmB1,
+                                                            const __grid_constant__ CUtensorMap tmB2,
+                                                            const AttnParams p) {
+  constexpr int S_ = 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  float* xch = reinterpret_cast<float*>(smem + A2_XCH_OFFSET);
+  uint64_t* full1 = reinterpret_cast<uint64_t*>(smem + A2_BAR_OFFSET);
+  uint64_t* empty1 = full1 + 3;
+  uint64_t* s_full = empty1 + 3;
+  uint64_t* p_ready = s_full + 1;    // [2]: P_A / P_B written
+  uint64_t* full2 = p_ready + 2;     // [2]
+  uint64_t* empty2 = full2 + 2;      // [2]
+  uint64_t* o_full = empty2 + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y;
+  const int row0 = b * S_;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA);
+    prefetch_tmap(&tmB1);
+    prefetch_tmap(&tmB2);
+    for (int s = 0; s < 3; ++s) { mbar_init(&full1[s], 1); mbar_init(&empty1[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&full2[s], 1); mbar_init(&empty2[s], 1); mbar_init(&p_ready[s], 8); }
+    mbar_init(s_full, 1);
+    mbar_init(o_full, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      bool ok = true;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < p.nkb1 && ok; ++kb) {
+        ok = mbar_wait(&empty1[st], ph ^ 1, p.error_flag, 21);
+        if (!ok) break;
+        uint8_t* sq = smem + st * A2_REGION;
+        mbar_expect_tx(&full1[st], 2u * AT_A_BYTES + S_ * 128);
+        tma_load_3d(&tmA, &full1[st], sq, kb * 64, row0, 0);
+        tma_load_3d(&tmA, &full1[st], sq + AT_A_BYTES, kb * 64, row0 + 128, 0);
+        tma_load_3d(&tmB1, &full1[st], sq + 2 * AT_A_BYTES, kb * 64, row0, 0);
+        if (++st == 3) { st = 0; ph ^= 1; }
+      }
+      // the V ring lives in R0, which the score MMAs read until the last of them has retired
+      if (ok) ok = mbar_wait(s_full, 0, p.error_flag, 22);
+      const int nslab = p.C / 64;
+      st = 0; ph = 0;
+      for (int kb = 0; kb < p.nkb2 && ok; ++kb) {
+        ok = mbar_wait(&empty2[st], ph ^ 1, p.error_flag, 21);
+        if (!ok) break;
+        uint8_t* sv = smem + st * 32768;
+        mbar_expect_tx(&full2[st], (uint32_t)nslab * 8192u);
+        for (int j = 0; j < nslab; ++j) tma_load_3d(&tmB2, &full2[st], sv + j * 8192, j * 64, row0 + kb * 64, 0);
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      bool ok = true;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int kb = 0; kb < p.nkb1 && ok; ++kb) {
+        ok = mbar_wait(&full1[st], ph, p.error_flag, 23);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t sq = smem_u32(smem + st * A2_REGION), sk = sq + 2 * AT_A_BYTES;
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk)
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + blk * 256, make_desc(sq + blk * AT_A_BYTES + k * 32, 1, 64), make_desc(sk + k * 32, 1, 64),
+                     p.idesc1, (kb | k) ? 1u : 0u);
+        umma_commit(&empty1[st]);
+        if (++st == 3) { st = 0; ph ^= 1; }
+      }
+      if (ok) umma_commit(s_full);
+      // both P tiles in place (and with them the guarantee that every score has been read out of TMEM)
+      if (ok) ok = mbar_wait(&p_ready[0], 0, p.error_flag, 24);
+      if (ok) ok = mbar_wait(&p_ready[1], 0, p.error_flag, 24);
+      tc_fence_after();
+      st = 0; ph = 0;
+      for (int kb = 0; kb < p.nkb2 && ok; ++kb) {
+        ok = mbar_wait(&full2[st], ph, p.error_flag, 23);
+        if (!ok) break;
+        tc_fence_after();
+        const uint32_t sv = smem_u32(smem + st * 32768);
+#pragma unroll
+        for (int blk = 0; blk < 2; ++blk) {
+          const uint32_t sp = smem_u32(smem + (1 + blk) * A2_REGION);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_f16(tmem_base + blk * 256, make_desc(sp + kb * 16384 + k * 32, 1, 64), make_desc(sv + k * 2048, 512, 64),
+                     p.idesc2, (kb | k) ? 1u : 0u);
+        }
+        umma_commit(&empty2[st]);
+        if (++st == 2) { st = 0; ph ^= 1; }
+      }
+      if (ok) umma_commit(o_full);
+    }
+  } else {
+    const int q = warp & 3, h = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+    bool ok = mbar_wait(s_full, 0, p.error_flag, 25);
+    tc_fence_after();
+    if (ok) {
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        attn_row_op<S_, MODE>(trow + blk * 256 + h * (S_ / 2), smem + (1 + blk) * A2_REGION, xch, r, h, (int64_t)row0 + blk * 128 + r, p);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_ready[blk]);
+      }
+      ok = mbar_wait(o_full, 0, p.error_flag, 26);
+      tc_fence_after();
+      if (ok) {
+        float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (CW + 4);   // every MMA has retired: all three regions are free
+        EpiArgs e{nullptr, nullptr, nullptr, 0, 1.0f, p.y, p.ld_y, 0};
+#pragma unroll 1
+        for (int blk = 0; blk < 2; ++blk) {
+          const int64_t grow = (int64_t)row0 + blk * 128 + r;
+          epilogue_warp<CW>(trow + blk * 256 + h * CW, stage, lane, grow, grow, true, h * CW, e, nullptr, 0, 1);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int CW, int MODE>
+static int attn2_launch_t(const CUtensorMap& ma, const CUtensorMap& mb1, const CUtensorMap& mb2, const AttnParams& p, int B,
+                          cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(umma_attn2_kernel<CW, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
+    attr_set = true;
+  }
+  cudaError_t e = launch_pdl(umma_attn2_kernel<CW, MODE>, dim3(1, B), dim3(320), A2_SMEM, st, ma, mb1, mb2, p);
+  if (e != cudaSuccess) { set_error("fused attention (per-image) launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+  count_launch(1);
+  return BD_OK;
 }
 
 // =============================================================================================================
@@ -487,6 +680,14 @@ int attn_fused_launch(int mode, const void* a, int64_t ld_a, const void* b1, con
     if (!make_map(&mb1, b1, 3, dims, str, box1)) return BD_ERR_CUDA;
     uint32_t box2[3] = {64, 64, 1};
     if (!make_map(&mb2, b2, 3, dims, str, box2)) return BD_ERR_CUDA;
+  }
+  if (S == 256 && !getenv("BD_ATTN_V1")) {
+#define BD_ATTN2_CASE(CC)                                                                                          \
+  if (C == CC) return mode == 0 ? attn2_launch_t<CC / 2, 0>(ma, mb1, mb2, p, B, st) : attn2_launch_t<CC / 2, 1>(ma, mb1, mb2, p, B, st);
+    BD_ATTN2_CASE(256)
+    BD_ATTN2_CASE(128)
+    BD_ATTN2_CASE(64)
+#undef BD_ATTN2_CASE
   }
 #define BD_ATTN_CASE(SS, CC)                                                                          \
   if (S == SS && C == CC)                                                                             \

@@ -31,10 +31,12 @@ def run(fn, n=40):
 
 
 res = {}
-for fused in (False, True):
-    if fused:
-        os.environ.pop("BD_NO_ATTN_FUSED", None)
-    else:
+for fused in (False, "v1", True):
+    os.environ.pop("BD_NO_ATTN_FUSED", None)
+    os.environ.pop("BD_ATTN_V1", None)
+    if fused == "v1":
+        os.environ["BD_ATTN_V1"] = "1"      # one-tile-per-CTA fused kernels
+    elif not fused:
         os.environ["BD_NO_ATTN_FUSED"] = "1"
     l0 = ops.launch_count()
     tf = run(lambda i: ops.attention_fwd(qkvs[i], probs[i], outs[i], work, B, S, C, 1, scale, impl=_lib.BD_IMPL_UMMA))
@@ -42,6 +44,6 @@ for fused in (False, True):
     tb = run(lambda i: ops.attention_bwd(qkvs[i], probs[i], dos[i], dqkvs[i], work, B, S, C, 1, scale, impl=_lib.BD_IMPL_UMMA))
     l2 = ops.launch_count()
     res[fused] = (outs[0].clone(), probs[0].clone(), dqkvs[0].clone())
-    print(f"{'fused' if fused else 'unfused'} B={B} S={S} C={C}: fwd {tf:.1f} us ({(l1 - l0) // 44} launches), bwd {tb:.1f} us ({(l2 - l1) // 44} launches), umma_error={_lib.lib().bd_umma_error()}", flush=True)
+    print(f"{'fused (per-image)' if fused is True else 'fused v1' if fused else 'unfused'} B={B} S={S} C={C}: fwd {tf:.1f} us ({(l1 - l0) // 44} launches), bwd {tb:.1f} us ({(l2 - l1) // 44} launches), umma_error={_lib.lib().bd_umma_error()}", flush=True)
 a, b = res[False], res[True]
 print("max |fused - unfused|: out %.3g probs %.3g dqkv %.3g" % tuple(float((x.float() - y.float()).abs().max()) for x, y in zip(a, b)))

@@ -504,15 +504,19 @@ def test_upsample_add_colsum(ops):
 @pytest.mark.parametrize("impl,B,S,C,heads", [("simt", 3, 64, 64, 8), ("simt", 2, 16, 256, 1), ("simt", 2, 256, 256, 1),
                                               ("umma", 3, 256, 256, 1), ("umma", 2, 256, 512, 1), ("umma", 1, 128, 64, 1),
                                               ("umma", 5, 256, 128, 1), ("umma", 2, 128, 256, 1), ("umma", 19, 256, 64, 1),
-                                              ("umma_unfused", 3, 256, 256, 1)])
+                                              ("umma_unfused", 3, 256, 256, 1), ("umma_v1", 3, 256, 256, 1), ("umma_v1", 5, 256, 64, 1)])
 def test_attention_fwd_bwd(ops, impl, B, S, C, heads):
     im = ops.L.BD_IMPL_SIMT if impl == "simt" else ops.L.BD_IMPL_UMMA
     # S in {128, 256}, C in {64, 128, 256}: ONE fused tcgen05 kernel forward (QK^T -> softmax -> PV) and one for the
     # data-gradient half of backward (umma_attn.cu); BD_NO_ATTN_FUSED=1 = the three-launch path it replaced
+    # S = 256 defaults to the per-image kernel (one CTA = both query blocks of an image, K / V fetched once);
+    # BD_ATTN_V1=1 = the one-tile-per-CTA kernel that also serves S = 128
+    os.environ.pop("BD_NO_ATTN_FUSED", None)
+    os.environ.pop("BD_ATTN_V1", None)
     if impl == "umma_unfused":
         os.environ["BD_NO_ATTN_FUSED"] = "1"
-    else:
-        os.environ.pop("BD_NO_ATTN_FUSED", None)
+    elif impl == "umma_v1":
+        os.environ["BD_ATTN_V1"] = "1"
     launches0 = ops.launch_count()
     torch.manual_seed(0)
     d = C // heads
@@ -523,7 +527,7 @@ def test_attention_fwd_bwd(ops, impl, B, S, C, heads):
     work = torch.empty(ops.L.load().bd_attention_bwd_workspace_bytes(B, S, C, heads), dtype=torch.uint8, device="cuda")
     ops.attention_fwd(qkv, probs, out, work, B, S, C, heads, scale, impl=im)
     assert ops.umma_error() == 0
-    if impl == "umma" and C <= 256:
+    if impl in ("umma", "umma_v1") and C <= 256:
         assert ops.launch_count() - launches0 == 1       # fused: a single launch
     q32 = qkv.float().requires_grad_(True)
     q, k, v = q32[..., :C], q32[..., C:2 * C], q32[..., 2 * C:]
@@ -539,6 +543,7 @@ def test_attention_fwd_bwd(ops, impl, B, S, C, heads):
     assert ops.umma_error() == 0
     assert (dqkv.float() - q32.grad).abs().max() < 6e-3 * max(1.0, float(q32.grad.abs().max()))
     os.environ.pop("BD_NO_ATTN_FUSED", None)
+    os.environ.pop("BD_ATTN_V1", None)
 
 
 # ------------------------------------------------------------------------------------------------
