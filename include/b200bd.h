@@ -202,7 +202,8 @@ int bd_conv_fwd_gn_sums_supported(const bd_conv_args* a);
  * MN-major operand).  `residual` is added (gradient fan-in), x2/w2 unused.  Uses the same struct:
  * x:=dy, y:=dx, Cin/Cout keep their FORWARD meaning.                                                    */
 int bd_conv_dgrad(const bd_conv_args* a, void* stream);
-/* wgrad: dw f32 in the packed layout [tap][Cout][Cin] (+)= sum over pixels (split-K, fp32 atomics);
+/* wgrad: dw f32 in the packed layout [tap][Cout][Cin] (+)= sum over pixels (split-K; the partial tiles meet in dw through
+ * vector reductions, red.global.add.v4.f32 -- order noise in the last bits, no scalar atomics);
  * dbias (Cout) f32 nullable.  x (B,H,W,Cin) f16 view, dy (B,Ho,Wo,Cout) f16 view.                      */
 int bd_conv_wgrad(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, float* dw, float* dbias,
                   int B, int H, int W, int Cin, int Cout, int ksize, int mode, int pad, int accumulate, int impl,
@@ -247,6 +248,9 @@ int bd_add_f16(const void* a, int64_t ld_a, const void* b, int64_t ld_b, void* y
  * K7  D/models/attention.py:135-162: softmax_fp32(q k^T * scale) v on the fused-QKV buffer
  * qkv: (B, S, 3C) f16 with ld; heads split C as in reshape_heads_to_batch_dim (:77-82).
  * probs (B*heads, S, S) f16 is saved for backward (nullable in inference).  out: (B,S,C) f16 view.
+ * One head, S in {128, 256}, C in {64, 128, 256}: ONE tcgen05 kernel forward (QK^T in TMEM -> softmax in registers -> P as
+ * the shared-memory A operand of PV; csrc/umma_attn.cu), two backward (dP -> dS -> dQ; dK + dV); S = 256 runs one CTA per
+ * image.  Other single-head tcgen05-tileable shapes: GEMM + softmax + GEMM launches; everything else: CUDA cores.
  * ---------------------------------------------------------------------------------------------- */
 size_t bd_attention_fwd_workspace_bytes(int B, int S, int C, int heads);
 int bd_attention_fwd(const void* qkv, int64_t ld_qkv, void* probs, void* out, int64_t ld_out, void* work, int B, int S,
