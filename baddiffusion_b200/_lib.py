@@ -71,6 +71,8 @@ _SIGS = {
     "bd_silu_bwd_f32": (i32, [vp, vp, vp, sz, vp]),
     "bd_silu_f32_to_f16": (i32, [vp, vp, sz, vp]),
     "bd_conv_in_fwd": (i32, [vp, vp, vp, vp, i64, i32, i32, i32, i32, i32, vp]),
+    "bd_conv_in_fwd_gn_sums_supported": (i32, [i32, i32, i32, i32]),
+    "bd_conv_in_fwd_sums": (i32, [vp, vp, vp, vp, i64, vp, i64, i32, i32, i32, i32, i32, vp]),
     "bd_conv_in_wgrad": (i32, [vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp]),
     "bd_conv_out_fwd": (i32, [vp, i64, vp, vp, vp, i32, i32, i32, i32, i32, vp]),
     "bd_conv_out_bwd": (i32, [vp, i64, vp, vp, vp, i64, vp, vp, i32, i32, i32, i32, i32, i32, vp]),

@@ -32,6 +32,7 @@ struct FpropCall {
   int ntap_override;
   int tap_dx[9], tap_dy[9], tap_z[9];
   int64_t out_sn, out_sh, out_sw, out_off;
+  float* gn_sums; int64_t ld_sums;
 };
 struct WgradCall {
   const void* a; int64_t ld_a; int Mtot;
@@ -64,6 +65,7 @@ int conv3_supported(const Conv3Call& c);
 int conv3_gn_sums_supported(const Conv3Call& c);
 int conv3_launch(const Conv3Call& c, cudaStream_t st);
 int fprop_supported(const FpropCall& c);
+int fprop_gn_sums_supported(const FpropCall& c);
 int fprop_launch(const FpropCall& c, cudaStream_t st);
 int wgrad_supported(const WgradCall& c);
 int wgrad_launch(const WgradCall& c, cudaStream_t st);
@@ -159,24 +161,7 @@ int bd_init(void) {
 }
 int bd_umma_error(void) { return umma::read_error_flag(); }
 
-static umma::Conv3Call conv3_call_fwd(const bd_conv_args* a) {
-  umma::Conv3Call h;
-  memset(&h, 0, sizeof(h));
-  h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cin; h.a2 = a->x2; h.ld_a2 = a->ld_x2; h.Ca2 = a->Cin2;
-  h.NB = a->B; h.H = a->H; h.W = a->W; h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.b2 = a->w2; h.ld_b2 = a->Cin2;
-  h.N = a->Cout; h.b_mn = false; h.flip = false;
-  h.bias = a->bias; h.bias2 = a->bias2; h.rowbias = a->rowbias; h.ld_rowbias = a->ld_rowbias;
-  h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y;
-  h.out_f32 = a->out_dtype == BD_OUT_F32;
-  h.gn_sums = a->gn_sums; h.ld_sums = a->ld_sums;
-  return h;
-}
-
-int bd_conv_fwd(const bd_conv_args* a, void* stream) {
-  int rc = check_conv(a, "bd_conv_fwd");
-  if (rc) return rc;
-  if (a->B == 0) return BD_OK;
-  cudaStream_t st = (cudaStream_t)stream;
+static umma::FpropCall fprop_call_fwd(const bd_conv_args* a) {
   umma::FpropCall c;
   memset(&c, 0, sizeof(c));
   c.a = a->x; c.ld_a = a->ld_x; c.Ca = a->Cin;
@@ -197,6 +182,28 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
     c.ntap_override = 9;
     for (int t = 0; t < 9; ++t) { c.tap_dy[t] = t / 3 - a->pad; c.tap_dx[t] = t % 3 - a->pad; c.tap_z[t] = t; }
   }
+  return c;
+}
+
+static umma::Conv3Call conv3_call_fwd(const bd_conv_args* a) {
+  umma::Conv3Call h;
+  memset(&h, 0, sizeof(h));
+  h.a = a->x; h.ld_a = a->ld_x; h.Ca = a->Cin; h.a2 = a->x2; h.ld_a2 = a->ld_x2; h.Ca2 = a->Cin2;
+  h.NB = a->B; h.H = a->H; h.W = a->W; h.b = a->w; h.ld_b = a->Cin; h.b_rows = a->Cout; h.b2 = a->w2; h.ld_b2 = a->Cin2;
+  h.N = a->Cout; h.b_mn = false; h.flip = false;
+  h.bias = a->bias; h.bias2 = a->bias2; h.rowbias = a->rowbias; h.ld_rowbias = a->ld_rowbias;
+  h.residual = a->residual; h.ld_res = a->ld_res; h.scale = a->out_scale; h.y = a->y; h.ld_y = a->ld_y;
+  h.out_f32 = a->out_dtype == BD_OUT_F32;
+  h.gn_sums = a->gn_sums; h.ld_sums = a->ld_sums;
+  return h;
+}
+
+int bd_conv_fwd(const bd_conv_args* a, void* stream) {
+  int rc = check_conv(a, "bd_conv_fwd");
+  if (rc) return rc;
+  if (a->B == 0) return BD_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  umma::FpropCall c = fprop_call_fwd(a);
   const bool s2ok = a->mode == BD_CONV_S1 || (a->H % 2 == 0 && a->W % 2 == 0 && !a->x2);
   const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
   if ((a->impl == BD_IMPL_UMMA || a->impl == BD_IMPL_UMMA_TILE) && !(can && bd_device_supported())) {
@@ -208,7 +215,7 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
     if (a->impl != BD_IMPL_UMMA_TILE && a->mode == BD_CONV_S1 && a->ksize == 3 && umma::conv3_supported(h)) {
       rc = umma::conv3_launch(h, st);   // halo-reuse kernel (umma_conv3.cu)
     } else {
-      if (a->gn_sums) { set_error("bd_conv_fwd: gn_sums is not supported on this kernel path (query bd_conv_fwd_gn_sums_supported)"); return BD_ERR_UNSUPPORTED; }
+      c.gn_sums = a->gn_sums; c.ld_sums = a->ld_sums;   // generic kernels: statistics in epilogue_warp (rejected there if unsupported)
       rc = umma::fprop_launch(c, st);
     }
     if (rc) return rc;
@@ -221,10 +228,16 @@ int bd_conv_fwd(const bd_conv_args* a, void* stream) {
 }
 
 int bd_conv_fwd_gn_sums_supported(const bd_conv_args* a) {
-  if (!a || a->impl == BD_IMPL_SIMT || a->impl == BD_IMPL_UMMA_TILE || a->mode != BD_CONV_S1 || a->ksize != 3) return 0;
+  if (!a || a->impl == BD_IMPL_SIMT || check_conv(a, "bd_conv_fwd_gn_sums_supported")) return 0;
   if (a->out_dtype != BD_OUT_F16 || !umma_allowed()) return 0;
   umma::Conv3Call h = conv3_call_fwd(a);
-  return umma::conv3_gn_sums_supported(h);
+  const bool halo = a->impl != BD_IMPL_UMMA_TILE && a->mode == BD_CONV_S1 && a->ksize == 3 && umma::conv3_supported(h);
+  if (halo) return umma::conv3_gn_sums_supported(h);   // bd_conv_fwd takes the halo-reuse kernels for this call
+  // otherwise the generic tcgen05 kernels, if bd_conv_fwd would run them at all (same conditions as there)
+  umma::FpropCall c = fprop_call_fwd(a);
+  const bool s2ok = a->mode == BD_CONV_S1 || (a->H % 2 == 0 && a->W % 2 == 0 && !a->x2);
+  const bool can = s2ok && a->ld_y % 8 == 0 && (!a->residual || a->ld_res % 8 == 0) && umma::fprop_supported(c);
+  return can && umma::fprop_gn_sums_supported(c);
 }
 
 int bd_conv_dgrad(const bd_conv_args* a, void* stream) {

@@ -23,12 +23,14 @@ constexpr int NW_PITCH = 12;    // patch row: 10 values + 2 pad -> three aligned
 __global__ void __launch_bounds__(256, 2) narrow_to_wide_kernel(const float* __restrict__ src, const float* __restrict__ w,
                                                                 int st_tap, int st_c, int st_o, int flip,
                                                                 const float* __restrict__ bias, __half* __restrict__ y,
-                                                                int64_t ldy, int B, int Cs, int H, int W, int Cw) {
+                                                                int64_t ldy, int B, int Cs, int H, int W, int Cw,
+                                                                float* __restrict__ gn_sums, int64_t ld_sums) {
   extern __shared__ __align__(16) float nw_smem[];
   const int K = Cs * 9, C8 = Cw / 8, PG = blockDim.x / C8;
   float* sw = nw_smem;                   // [K][Cw]
   float* sb = sw + K * Cw;               // [Cw]
   float* patch = sb + Cw;                // [PG][Cs*3][NW_PITCH]
+  float* gred = patch + PG * Cs * 3 * NW_PITCH;   // [PG][Cw][2], only when gn_sums (GroupNorm statistics of y, see bd_conv_args)
   for (int i = threadIdx.x; i < K * Cw; i += blockDim.x) {
     const int o = i % Cw, k = i / Cw, c = k / 9, t = k % 9;
     const int tap = flip ? 8 - t : t;
@@ -61,7 +63,9 @@ __global__ void __launch_bounds__(256, 2) narrow_to_wide_kernel(const float* __r
     }
     __syncthreads();
     const int64_t gid = tile * PG + g;
-    if (gid >= ngroups || g >= PG) continue;
+    const bool active = gid < ngroups && g < PG;
+    float gs1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gs2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (active) {
     float acc[NW_PX][8];
     {
       const float4 b0 = *reinterpret_cast<const float4*>(sb + v * 8), b1 = *reinterpret_cast<const float4*>(sb + v * 8 + 4);
@@ -95,7 +99,35 @@ __global__ void __launch_bounds__(256, 2) narrow_to_wide_kernel(const float* __r
     }
     __half* yp = y + gid * NW_PX * ldy + v * 8;
 #pragma unroll
-    for (int j = 0; j < NW_PX; ++j) *reinterpret_cast<half8*>(yp + j * ldy) = pack8(acc[j]);
+    for (int j = 0; j < NW_PX; ++j) {
+      const half8 hv = pack8(acc[j]);
+      *reinterpret_cast<half8*>(yp + j * ldy) = hv;
+      if (gn_sums) {
+        float f[8];
+        unpack8(hv, f);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gs1[k] += f[k]; gs2[k] = fmaf(f[k], f[k], gs2[k]); }
+      }
+    }
+    }  // active
+    if (gn_sums) {
+      // the tile's PG x 8 pixels belong to ONE image (launcher: H*W % (PG*8) == 0): fold the pixel groups through shared
+      // memory, one atomic per (tile, channel, quantity)
+      if (g < PG) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          gred[(g * Cw + v * 8 + k) * 2] = gs1[k];
+          gred[(g * Cw + v * 8 + k) * 2 + 1] = gs2[k];
+        }
+      }
+      __syncthreads();
+      const int64_t smp = (tile * PG * NW_PX) / ((int64_t)H * W);
+      for (int i = threadIdx.x; i < Cw * 2; i += blockDim.x) {
+        float t = 0.f;
+        for (int gg = 0; gg < PG; ++gg) t += gred[gg * Cw * 2 + i];
+        atomicAdd(gn_sums + smp * ld_sums + i, t);
+      }
+    }
   }
 }
 
@@ -386,10 +418,11 @@ static bool narrow_to_wide_ok(int Cs, int W, int Cw) {
 
 static bool narrow_to_wide_launch(const float* src, const float* w, int st_tap, int st_c, int st_o, int flip,
                                   const float* bias, __half* y, int64_t ldy, int B, int Cs, int H, int W, int Cw,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, float* gn_sums = nullptr, int64_t ld_sums = 0) {
   if (!narrow_to_wide_ok(Cs, W, Cw) || ldy % 8) return false;
   const int C8 = Cw / 8, PG = 256 / C8;
-  const size_t smem = ((size_t)Cs * 9 * Cw + Cw + (size_t)PG * Cs * 3 * NW_PITCH) * sizeof(float);
+  if (gn_sums && ((int64_t)H * W) % (PG * NW_PX)) return false;
+  const size_t smem = ((size_t)Cs * 9 * Cw + Cw + (size_t)PG * Cs * 3 * NW_PITCH + (gn_sums ? (size_t)PG * Cw * 2 : 0)) * sizeof(float);
   if (smem > 100 * 1024) return false;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
@@ -400,15 +433,21 @@ static bool narrow_to_wide_launch(const float* src, const float* w, int st_tap, 
   int grid = 2 * num_sms();
   if (grid > ntiles) grid = (int)ntiles;
   if (grid < 1) return true;
-  narrow_to_wide_kernel<<<grid, 256, smem, st>>>(src, w, st_tap, st_c, st_o, flip, bias, y, ldy, B, Cs, H, W, Cw);
+  narrow_to_wide_kernel<<<grid, 256, smem, st>>>(src, w, st_tap, st_c, st_o, flip, bias, y, ldy, B, Cs, H, W, Cw, gn_sums, ld_sums);
   count_launch(1);
   return true;
 }
 
 bool conv_in_fwd_fast(const float* x, const float* w, const float* bias, __half* y, int64_t ldy, int B, int Cin, int H,
-                      int W, int Cout, cudaStream_t st) {
+                      int W, int Cout, cudaStream_t st, float* gn_sums, int64_t ld_sums) {
   // packed [tap][Cout][Cin]: c = ci, o = co
-  return narrow_to_wide_launch(x, w, Cout * Cin, 1, Cin, 0, bias, y, ldy, B, Cin, H, W, Cout, st);
+  return narrow_to_wide_launch(x, w, Cout * Cin, 1, Cin, 0, bias, y, ldy, B, Cin, H, W, Cout, st, gn_sums, ld_sums);
+}
+bool conv_in_fwd_sums_ok(int Cin, int H, int W, int Cout) {
+  if (!narrow_to_wide_ok(Cin, W, Cout)) return false;
+  const int PG = 256 / (Cout / 8);
+  return ((int64_t)H * W) % (PG * NW_PX) == 0 &&
+         ((size_t)Cin * 9 * Cout + Cout + (size_t)PG * Cin * 3 * NW_PITCH + (size_t)PG * Cout * 2) * sizeof(float) <= 100 * 1024;
 }
 
 bool conv_out_dgrad_fast(const float* w, const float* dy, __half* dx, int64_t lddx, int B, int Cin, int H, int W, int Cout,

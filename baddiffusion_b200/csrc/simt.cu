@@ -646,7 +646,8 @@ __global__ void zero_f32_kernel(float* p, size_t n) {
 
 // fast paths for the UNet's own shapes (convio.cu)
 bool conv_in_fwd_fast(const float* x, const float* w, const float* bias, __half* y, int64_t ldy, int B, int Cin, int H,
-                      int W, int Cout, cudaStream_t st);
+                      int W, int Cout, cudaStream_t st, float* gn_sums, int64_t ld_sums);
+bool conv_in_fwd_sums_ok(int Cin, int H, int W, int Cout);
 bool conv_out_dgrad_fast(const float* w, const float* dy, __half* dx, int64_t lddx, int B, int Cin, int H, int W, int Cout,
                          cudaStream_t st);
 bool conv_out_fwd_fast(const __half* x, int64_t ldx, const float* w, const float* bias, float* y, int B, int Cin, int H,
@@ -776,11 +777,29 @@ int bd_bias_from_gsum(const void* jobs, int njobs, int max_c, int B, void* strea
   return BD_OK;
 }
 
+int bd_conv_in_fwd_gn_sums_supported(int Cin, int H, int W, int Cout) {
+  // off by default with the generic kernels' statistics (BD_GN_SUMS_GENERIC=1, see umma.cu fprop_gn_sums_supported)
+  return getenv("BD_NO_CONVIO") == nullptr && getenv("BD_NO_GN_SUMS") == nullptr && getenv("BD_GN_SUMS_GENERIC") != nullptr &&
+         conv_in_fwd_sums_ok(Cin, H, W, Cout);
+}
+
+int bd_conv_in_fwd_sums(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, float* gn_sums,
+                        int64_t ld_sums, int B, int Cin, int H, int W, int Cout, void* stream) {
+  BD_CHECK_ARG(x_nchw && w_packed && y && gn_sums && Cin > 0 && Cin <= 4 && Cout % 8 == 0 && ld_y % 8 == 0, "bd_conv_in_fwd_sums: bad argument");
+  if (!bd_conv_in_fwd_gn_sums_supported(Cin, H, W, Cout) ||
+      !conv_in_fwd_fast(x_nchw, w_packed, bias, (__half*)y, ld_y, B, Cin, H, W, Cout, (cudaStream_t)stream, gn_sums, ld_sums)) {
+    set_error("bd_conv_in_fwd_sums: shape outside the register-tiled kernel (query bd_conv_in_fwd_gn_sums_supported)");
+    return BD_ERR_UNSUPPORTED;
+  }
+  BD_CHECK_LAUNCH();
+  return BD_OK;
+}
+
 int bd_conv_in_fwd(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, int B, int Cin,
                    int H, int W, int Cout, void* stream) {
   BD_CHECK_ARG(x_nchw && w_packed && y && Cin > 0 && Cin <= 4 && Cout % 8 == 0 && ld_y % 8 == 0, "bd_conv_in_fwd: need Cin <= 4, Cout %% 8 == 0");
   if (getenv("BD_NO_CONVIO") == nullptr &&
-      conv_in_fwd_fast(x_nchw, w_packed, bias, (__half*)y, ld_y, B, Cin, H, W, Cout, (cudaStream_t)stream)) {
+      conv_in_fwd_fast(x_nchw, w_packed, bias, (__half*)y, ld_y, B, Cin, H, W, Cout, (cudaStream_t)stream, nullptr, 0)) {
     BD_CHECK_LAUNCH();
     return BD_OK;
   }

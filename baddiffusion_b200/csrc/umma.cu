@@ -58,6 +58,8 @@ struct FpropParams {
   void* y;
   int64_t ld_y;
   int out_f32;
+  float* gn_sums;        // GNS kernels: GroupNorm statistics of the output (see EpiArgs)
+  int64_t ld_sums;
   int* error_flag;
   int dbg_shift, dbg_boff;  // bring-up experiment: A tile loaded dbg_shift rows early, descriptor start moved back
 };
@@ -91,7 +93,7 @@ struct Smem {
 // =============================================================================================
 // fprop-style kernel
 // =============================================================================================
-template <int BN, int kStages, bool B_MN>
+template <int BN, int kStages, bool B_MN, bool GNS = false>   // GNS: the epilogue also accumulates GroupNorm statistics
 __global__ void __launch_bounds__(320, BN == 256 ? 1 : 2) umma_fprop_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                             const __grid_constant__ CUtensorMap tmA1,
                                                             const __grid_constant__ CUtensorMap tmB0,
@@ -220,16 +222,16 @@ __global__ void __launch_bounds__(320, BN == 256 ? 1 : 2) umma_fprop_kernel(cons
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
     tc_fence_after();
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (BN / 2 + 4);  // operand stages are free now
-    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32, p.gn_sums, p.ld_sums};
     if (S == 1) {
       if (ok)
-        epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
-                              n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+        epilogue_warp<BN / 2, GNS>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
+                                   n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
     } else {
       if (ok) epilogue_stage_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane);
       cluster_sync_all();   // every rank's partial tile is staged (all threads of the cluster take part, see below)
-      epilogue_splitk_finish_warp<BN / 2>(stage, lane, S, rank, m, mlin, valid, n_tile * BN + half * (BN / 2), e, p.rowbias,
-                                          p.ld_rowbias, p.HW, CM, mrank);
+      epilogue_splitk_finish_warp<BN / 2, GNS>(stage, lane, S, rank, m, mlin, valid, n_tile * BN + half * (BN / 2), e, p.rowbias,
+                                               p.ld_rowbias, p.HW, CM, mrank);
     }
   }
   if (S > 1) {
@@ -268,7 +270,7 @@ struct SmemP {
   static constexpr int kTotal = kBarOffset + (2 * kStages + 4) * 8 + 16 + 1024;
 };
 
-template <int BN, int kStages, bool B_MN>
+template <int BN, int kStages, bool B_MN, bool GNS = false>
 __global__ void __launch_bounds__(320, 1) umma_fprop_persistent_kernel(const __grid_constant__ CUtensorMap tmA0,
                                                                        const __grid_constant__ CUtensorMap tmA1,
                                                                        const __grid_constant__ CUtensorMap tmB0,
@@ -383,7 +385,7 @@ __global__ void __launch_bounds__(320, 1) umma_fprop_persistent_kernel(const __g
     const int r = q * 32 + lane;
     const int dn = r / (p.bw * p.bh), dh = (r / p.bw) % p.bh, dw = r % p.bw;
     float* stage = reinterpret_cast<float*>(smem + L::kEpiOffset) + (warp - 2) * 32 * (BN / 2 + 4);
-    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32};
+    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32, p.gn_sums, p.ld_sums};
     uint32_t fph[2] = {0, 0};
     bool ok = true;
     int lt = 0;
@@ -399,8 +401,8 @@ __global__ void __launch_bounds__(320, 1) umma_fprop_persistent_kernel(const __g
       if (!ok) break;
       fph[buf] ^= 1;
       tc_fence_after();
-      epilogue_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2), stage, lane, m, mlin, valid,
-                            n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+      epilogue_warp<BN / 2, GNS>(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2), stage, lane, m, mlin, valid,
+                                 n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -633,11 +635,11 @@ static bool pick_box(int H, int W, int pixels, int* bw, int* bh, int* bn) {
 // kStages = 3 (3 x 32 KB): two CTAs per SM, so one drains its accumulator while the other streams operands -- for grids
 // with more CTAs than SMs.  kStages = 6: grids that put at most one CTA on an SM anyway (the 8x8 / 4x4 levels) are a
 // chain of TMA round trips (a k-block's MMAs take 256 cycles, a stage refill ~1 us): twice the loads in flight.
-template <int BN, bool B_MN, int kStages>
+template <int BN, bool B_MN, int kStages, bool GNS = false>
 static int launch_fprop_t(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& b, const CUtensorMap& b1,
                           const FpropParams& p, dim3 grid, cudaStream_t st) {
   using L = Smem<BN, kStages>;
-  auto kern = umma_fprop_kernel<BN, kStages, B_MN>;
+  auto kern = umma_fprop_kernel<BN, kStages, B_MN, GNS>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kTotal);
@@ -685,6 +687,7 @@ struct FpropCall {
   int ntap_override;       // > 0: explicit tap list instead of the ks*ks grid
   int tap_dx[9], tap_dy[9], tap_z[9];
   int64_t out_sn, out_sh, out_sw, out_off;  // output pixel addressing (0 = dense NHWC)
+  float* gn_sums; int64_t ld_sums;   // forward only: GroupNorm statistics of y accumulated in the epilogue (nullable)
 };
 
 int fprop_supported(const FpropCall& c) {
@@ -699,9 +702,22 @@ int fprop_supported(const FpropCall& c) {
   return 1;
 }
 
+// in-epilogue GroupNorm statistics on the generic kernels: forward (K-major weights), fp16 output, whole 8-pixel row groups
+// of one image per epilogue iteration (HW % 8 == 0), not the batched (attention) GEMMs.  OFF by default (BD_GN_SUMS_GENERIC=1
+// enables): with them ALL 51 forward GroupNorms of the CIFAR10 UNet become streaming passes, but measured inside the step
+// (scripts/ab_step.py) that LOSES 0.05 ms in training and changes nothing in sampling -- at 8x8 / 4x4 the GroupNorm launches
+// are latency-, not reduction-bound, and the atomics make even the tiny test configs run-to-run non-reproducible.
+int fprop_gn_sums_supported(const FpropCall& c) {
+  const int HW = c.HW_rowbias > 0 ? c.HW_rowbias : c.H * c.W;
+  return fprop_supported(c) && !c.b_mn && !c.batched && !c.out_f32 && HW % 8 == 0 && c.N % 128 == 0 && !getenv("BD_NO_GN_SUMS") &&
+         getenv("BD_GN_SUMS_GENERIC");
+}
+
 int fprop_launch(const FpropCall& c, cudaStream_t st) {
   FpropParams p;
   memset(&p, 0, sizeof(p));
+  if (c.gn_sums && !fprop_gn_sums_supported(c)) { set_error("umma fprop: gn_sums is not supported for this launch"); return BD_ERR_UNSUPPORTED; }
+  p.gn_sums = c.gn_sums; p.ld_sums = c.ld_sums;
   if (!pick_box(c.H, c.W, BM, &p.bw, &p.bh, &p.bn)) { set_error("umma fprop: geometry %dx%d does not tile", c.H, c.W); return BD_ERR_UNSUPPORTED; }
   p.tiles_w = c.W / p.bw;
   p.tiles_h = c.H / p.bh;
@@ -833,7 +849,11 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
     const int nt = c.N / BN;
     const int ctas = num_sms();
     static bool pattr[2] = {false, false};
-    if (c.b_mn) {
+    if (c.gn_sums) {
+      static bool gattr = false;
+      if (!gattr) { cudaFuncSetAttribute(umma_fprop_persistent_kernel<128, kSt, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal); gattr = true; }
+      launch_pdl(umma_fprop_persistent_kernel<128, kSt, false, true>, dim3(ctas), dim3(320), (size_t)LP::kTotal, st, ma0, ma1, mb, mb1, p, m_tiles, nt);
+    } else if (c.b_mn) {
       if (!pattr[1]) { cudaFuncSetAttribute(umma_fprop_persistent_kernel<128, kSt, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, LP::kTotal); pattr[1] = true; }
       launch_pdl(umma_fprop_persistent_kernel<128, kSt, true>, dim3(ctas), dim3(320), (size_t)LP::kTotal, st, ma0, ma1, mb, mb1, p, m_tiles, nt);
     } else {
@@ -844,6 +864,11 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
     return BD_OK;
   }
   const bool deep = (long long)grid.x * grid.y * grid.z <= num_sms() && p.total_kblocks / p.splits >= 6 && !getenv("BD_NO_DEEP_RING");
+  if (c.gn_sums) {   // forward, BN in {128, 256} (checked above)
+    if (BN == 256) return launch_fprop_t<256, false, 4, true>(ma0, ma1, mb, mb1, p, grid, st);
+    if (deep) return launch_fprop_t<128, false, 6, true>(ma0, ma1, mb, mb1, p, grid, st);
+    return launch_fprop_t<128, false, 3, true>(ma0, ma1, mb, mb1, p, grid, st);
+  }
   if (BN == 256) {
     if (c.b_mn) launch_fprop_t<256, true, 4>(ma0, ma1, mb, mb1, p, grid, st); else launch_fprop_t<256, false, 4>(ma0, ma1, mb, mb1, p, grid, st);
   } else if (BN == 128) {

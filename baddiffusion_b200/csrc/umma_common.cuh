@@ -186,11 +186,38 @@ struct EpiArgs {
   void* y;
   int64_t ld_y;
   int out_f32;
+  // GroupNorm statistics of the output (GNS instantiations of the epilogues only): gn_sums[sample * ld_sums + 2 * column
+  // + {0, 1}] += sum / sum of squares of the fp16-rounded outputs; sample = dense pixel index / HW
+  float* gn_sums = nullptr;
+  int64_t ld_sums = 0;
 };
+
+// Fold the per-lane channel partials of one sample over the lanes that hold the same 8 columns (lane = rsub * LPR + piece)
+// and add them to the statistics buffer (one red.global.add per (warp, sample, column, quantity)).  Warp-uniform call.
+template <int LPR>
+__device__ __forceinline__ void gn_sums_flush(float* gs1, float* gs2, float* dst, int lane) {
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+#pragma unroll
+    for (int o = LPR; o < 32; o <<= 1) {
+      gs1[k] += __shfl_xor_sync(0xffffffffu, gs1[k], o);
+      gs2[k] += __shfl_xor_sync(0xffffffffu, gs2[k], o);
+    }
+  }
+  if (lane < LPR && dst) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      atomicAdd(dst + 2 * k, gs1[k]);
+      atomicAdd(dst + 2 * k + 1, gs2[k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) gs1[k] = gs2[k] = 0.f;
+}
 
 // CW = number of accumulator columns this warp drains (a window of the tile starting at TMEM address `taddr`,
 // global column `col0`).  rowbias: base pointer (nullable); the per-row sample index is mlin / HW.
-template <int CW>
+template <int CW, bool GNS = false>
 __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict__ stage, int lane, int64_t m_own,
                                               int64_t mlin_own, bool valid_own, int col0, const EpiArgs& e,
                                               const float* __restrict__ rowbias, int64_t ld_rowbias, int HW) {
@@ -219,12 +246,23 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
     const float4 a = *reinterpret_cast<const float4*>(e.bias2 + col), b = *reinterpret_cast<const float4*>(e.bias2 + col + 4);
     bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w; bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
   }
+  // GNS: the RPI rows of one iteration belong to ONE sample (hosts enable it only for HW % 8 == 0 and tiles that hold whole
+  // pixel groups of an image), so the sample index is warp-uniform and a change of it flushes the partials of the previous one
+  float gs1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gs2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t cur_smp = -1;
 #pragma unroll 2
   for (int r0 = 0; r0 < 32; r0 += RPI) {
     const int row = r0 + rsub;
     const int64_t m = __shfl_sync(0xffffffffu, m_own, row);
     const int64_t mlin = __shfl_sync(0xffffffffu, mlin_own, row);
     const int valid = __shfl_sync(0xffffffffu, (int)valid_own, row);
+    if (GNS) {
+      const int64_t smp = __shfl_sync(0xffffffffu, valid ? mlin / HW : (int64_t)-1, 0);   // lane 0's row speaks for the iteration
+      if (smp != cur_smp) {
+        if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
+        cur_smp = smp;
+      }
+    }
     if (!valid) continue;
     const float* sp = stage + row * PITCH + piece * 8;
     const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
@@ -249,8 +287,19 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
       *reinterpret_cast<float4*>(yr) = make_float4(f[0], f[1], f[2], f[3]);
       *reinterpret_cast<float4*>(yr + 4) = make_float4(f[4], f[5], f[6], f[7]);
     } else {
-      *reinterpret_cast<half8*>(reinterpret_cast<__half*>(e.y) + m * e.ld_y + col) = pack8(f);
+      const half8 hv = pack8(f);
+      *reinterpret_cast<half8*>(reinterpret_cast<__half*>(e.y) + m * e.ld_y + col) = hv;
+      if (GNS) {   // statistics of the rounded values the consumer will read
+        float g[8];
+        unpack8(hv, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gs1[k] += g[k]; gs2[k] = fmaf(g[k], g[k], gs2[k]); }
+      }
     }
+  }
+  if (GNS) {
+    __syncwarp();
+    if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
   }
   __syncwarp();
 }
@@ -307,7 +356,7 @@ __device__ __forceinline__ void epilogue_stage_warp(uint32_t taddr, float* __res
 }
 
 // phase 2 (after the cluster barrier): rows r0 = RPI * i with i % S == rank
-template <int CW>
+template <int CW, bool GNS = false>
 __device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restrict__ stage, int lane, int S, int rank,
                                                             int64_t m_own, int64_t mlin_own, bool valid_own, int col0,
                                                             const EpiArgs& e, const float* __restrict__ rowbias,
@@ -326,11 +375,20 @@ __device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restr
     const float4 a = *reinterpret_cast<const float4*>(e.bias2 + col), b = *reinterpret_cast<const float4*>(e.bias2 + col + 4);
     bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w; bsum[4] += b.x; bsum[5] += b.y; bsum[6] += b.z; bsum[7] += b.w;
   }
+  float gs1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gs2[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // GNS: see epilogue_warp
+  int64_t cur_smp = -1;
   for (int it = rank; it < 32 / RPI; it += S) {
     const int row = it * RPI + rsub;
     const int64_t m = __shfl_sync(0xffffffffu, m_own, row);
     const int64_t mlin = __shfl_sync(0xffffffffu, mlin_own, row);
     const int valid = __shfl_sync(0xffffffffu, (int)valid_own, row);
+    if (GNS) {
+      const int64_t smp = __shfl_sync(0xffffffffu, valid ? mlin / HW : (int64_t)-1, 0);
+      if (smp != cur_smp) {
+        if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
+        cur_smp = smp;
+      }
+    }
     if (!valid) continue;
     const uint32_t sp = smem_u32(stage + row * PITCH + piece * 8);
     float f[8] = {bsum[0], bsum[1], bsum[2], bsum[3], bsum[4], bsum[5], bsum[6], bsum[7]};
@@ -360,8 +418,19 @@ __device__ __forceinline__ void epilogue_splitk_finish_warp(const float* __restr
       *reinterpret_cast<float4*>(yr) = make_float4(f[0], f[1], f[2], f[3]);
       *reinterpret_cast<float4*>(yr + 4) = make_float4(f[4], f[5], f[6], f[7]);
     } else {
-      *reinterpret_cast<half8*>(reinterpret_cast<__half*>(e.y) + m * e.ld_y + col) = pack8(f);
+      const half8 hv = pack8(f);
+      *reinterpret_cast<half8*>(reinterpret_cast<__half*>(e.y) + m * e.ld_y + col) = hv;
+      if (GNS) {
+        float g[8];
+        unpack8(hv, g);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { gs1[k] += g[k]; gs2[k] = fmaf(g[k], g[k], gs2[k]); }
+      }
     }
+  }
+  if (GNS) {
+    __syncwarp();
+    if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
   }
 }
 

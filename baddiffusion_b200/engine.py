@@ -80,8 +80,8 @@ class UNetEngine:
         self.side = (torch.cuda.Stream(device=self.dev)
                      if train and not os.environ.get("BD_NO_SIDE_STREAM") else None)
         # GroupNorm statistics accumulated by the producing convs (bd_conv_args.gn_sums): one arena, zeroed by ONE memset
-        # at the start of every forward; only layers at resolutions the halo-reuse 3x3 kernels serve (H % 32 == 0, 16 x 16) use it
-        self._sums_cap = 2 * batch * 32768 if (S % 32 == 0 and not os.environ.get("BD_NO_GN_SUMS")) else 0
+        # at the start of every forward
+        self._sums_cap = 2 * batch * 49152 if not os.environ.get("BD_NO_GN_SUMS") else 0
         self._sums_arena = torch.zeros(max(self._sums_cap, 1), device=self.dev)
         self._sums_used = 0
         self.gn_sums_layers = 0   # GroupNorms planned on the producer-statistics path (introspection / tests)
@@ -122,7 +122,7 @@ class UNetEngine:
     def new_sums(self, H, C):
         """(B, C, 2) slice of the statistics arena, or None where no producer could fill it."""
         n = self.B * C * 2
-        if (H % 32 and H != 16) or self._sums_used + n > self._sums_cap:
+        if (H * H) % 8 or self._sums_used + n > self._sums_cap:
             return None
         v = self._sums_arena[self._sums_used: self._sums_used + n].view(self.B, C, 2)
         self._sums_used += n
@@ -135,11 +135,13 @@ class UNetEngine:
             a.gs = torch.empty(self.B, C, device=self.dev)
         return a
 
-    def _conv3_sums(self, x_t, w, y_t, sums, residual=None, x2=None, w2=None):
-        """Plan time: `sums` if the 3x3 conv x_t -> y_t will run on a kernel whose epilogue accumulates them, else None."""
+    def _conv3_sums(self, x_t, w, y_t, sums, residual=None, x2=None, w2=None, ksize=3, mode=L.BD_CONV_S1, pad=0):
+        """Plan time: `sums` if the conv x_t -> y_t will run on a kernel whose epilogue accumulates them, else None."""
         if sums is None:
             return None
-        return sums if ops.conv_fwd_gn_sums_supported(x_t, w, y_t, ksize=3, residual=residual, x2=x2, w2=w2, impl=self.impl) else None
+        ok = ops.conv_fwd_gn_sums_supported(x_t, w, y_t, ksize=ksize, mode=mode, pad=pad, residual=residual, x2=x2, w2=w2,
+                                            impl=self.impl)
+        return sums if ok else None
 
     def _gn_fwd(self, x_t, y_t, gamma, beta, stats, silu, sums):
         """GroupNorm (+SiLU) forward: streaming apply over producer-accumulated statistics when `sums` is given, else the
@@ -272,7 +274,10 @@ class UNetEngine:
         h0 = skip_acts[0]  # (h is re-bound below: the closures must capture h0)
         w_in, b_in = self.P32("conv_in.weight"), self.P32("conv_in.bias")
         self.named["conv_in."] = h0
-        self.fwd.append(lambda: ops.conv_in_fwd(self.io["x"], w_in, b_in, h0.t))
+        h0_sums = h0.sums if (h0.sums is not None and self.impl != L.BD_IMPL_SIMT
+                              and ops.conv_in_fwd_gn_sums_supported(cfg.in_channels, S, S, boc[0])) else None
+        h0.sums_ok = h0_sums is not None
+        self.fwd.append(lambda: ops.conv_in_fwd(self.io["x"], w_in, b_in, h0.t, gn_sums=h0_sums))
         if self.train:
             gw_in, gb_in = self.G32("conv_in.weight"), self.G32("conv_in.bias")
             self._bwd_emitters.append(lambda: self.bwd.append(
@@ -508,12 +513,14 @@ class UNetEngine:
 
         x_sums = x.sums if (x.sums_ok and x.sums is not None) else None
         self.gn_sums_layers += x_sums is not None
+        out_sums = self._conv3_sums(ao, wp, out.t, out.sums, residual=x.t, ksize=1)
+        out.sums_ok = out_sums is not None
 
         def f():
             self._gn_fwd(x.t, a, gnw, gnb, st, False, x_sums)
             ops.conv_fwd(a, wqkv, qkv, ksize=1, bias=bqkv, impl=impl)
             ops.attention_fwd(qkv.view(B, S, 3 * C), probs, ao.view(B, S, C), work, B, S, C, heads, sm_scale, impl=impl)
-            ops.conv_fwd(ao, wp, out.t, ksize=1, bias=bp, residual=x.t, scale=scale, impl=impl)
+            ops.conv_fwd(ao, wp, out.t, ksize=1, bias=bp, residual=x.t, scale=scale, impl=impl, gn_sums=out_sums)
 
         self.fwd.append(f)
         if not self.train:
@@ -559,7 +566,9 @@ class UNetEngine:
             raise NotImplementedError("downsample_padding must be 0 or 1")
         w, b = self.W16(p + "weight"), self.P32(p + "bias")
         self.named[p] = out
-        self.fwd.append(lambda: ops.conv_fwd(x.t, w, out.t, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad, bias=b))
+        out_sums = self._conv3_sums(x.t, w, out.t, out.sums, mode=L.BD_CONV_S2_PAD01, pad=pad)
+        out.sums_ok = out_sums is not None
+        self.fwd.append(lambda: ops.conv_fwd(x.t, w, out.t, ksize=3, mode=L.BD_CONV_S2_PAD01, pad=pad, bias=b, gn_sums=out_sums))
         if not self.train:
             return
 

@@ -251,10 +251,20 @@ def silu_f32_to_f16(x, y):
     check(L.lib().bd_silu_f32_to_f16(_p(x), _p(y), x.numel(), _s()))
 
 
-def conv_in_fwd(x_nchw, w_packed, bias, y):
+def conv_in_fwd(x_nchw, w_packed, bias, y, gn_sums=None):
+    """gn_sums: optional (B, Cout, 2) f32 view that receives (+=) the GroupNorm statistics of y (see conv_fwd)."""
     B, Cin, H, W = x_nchw.shape
+    if gn_sums is not None:
+        assert gn_sums.stride(2) == 1 and gn_sums.stride(1) == 2
+        check(L.lib().bd_conv_in_fwd_sums(_p(x_nchw), _p(w_packed), _p(bias), y.data_ptr(), y.stride(2), gn_sums.data_ptr(),
+                                          gn_sums.stride(0), B, Cin, H, W, y.shape[3], _s()))
+        return
     check(L.lib().bd_conv_in_fwd(_p(x_nchw), _p(w_packed), _p(bias), y.data_ptr(), y.stride(2), B, Cin, H, W,
                                  y.shape[3], _s()))
+
+
+def conv_in_fwd_gn_sums_supported(Cin, H, W, Cout) -> bool:
+    return bool(L.lib().bd_conv_in_fwd_gn_sums_supported(Cin, H, W, Cout))
 
 
 def conv_in_wgrad(x_nchw, dy, dw, dbias, accumulate=False):

@@ -228,6 +228,11 @@ int bd_silu_f32_to_f16(const float* x, void* y, size_t n, void* stream);
  * of these two layers are f32 in the packed [tap][Cout][Cin] layout.                                  */
 int bd_conv_in_fwd(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, int B, int Cin,
                    int H, int W, int Cout, void* stream);
+/* conv_in whose epilogue also accumulates the GroupNorm statistics of y (layout as bd_conv_args.gn_sums): the first
+ * ResnetBlock2D's norm1 and the last up-block concat then need no reduction pass either.  Query first. */
+int bd_conv_in_fwd_gn_sums_supported(int Cin, int H, int W, int Cout);
+int bd_conv_in_fwd_sums(const float* x_nchw, const float* w_packed, const float* bias, void* y, int64_t ld_y, float* gn_sums,
+                        int64_t ld_sums, int B, int Cin, int H, int W, int Cout, void* stream);
 int bd_conv_in_wgrad(const float* x_nchw, const void* dy, int64_t ld_dy, float* dw, float* dbias, int B, int Cin,
                      int H, int W, int Cout, int accumulate, void* stream);
 /* conv_out (f16 NHWC in -> Cout=3 f32 NCHW eps_hat), unet_2d.py:217,314; and its backward.  bd_conv_out_bwd: dx nullable

@@ -203,7 +203,7 @@ def test_two_rank_nccl_gradient_matches_global_batch(tmp_path):
         assert v[mode]["param_update_rel"] <= 2.5e-2 and v[mode]["param_max_abs"] <= 4.5e-4, v
 
 
-def test_trainer_u8_input_equals_fp32_input():
+def test_trainer_u8_input_equals_fp32_input(monkeypatch):
     """SURVEY 8f n2 end to end: Trainer(u8_input=True).step_u8(decoded pixels, coins) == Trainer.step(the fp32 NCHW batch
     the reference's DataLoader would have produced from the same pixels) -- bitwise equal loss (same x_noisy / target)."""
     from baddiffusion_b200.dataset import Backdoor, draw_flips
@@ -212,6 +212,7 @@ def test_trainer_u8_input_equals_fp32_input():
     from baddiffusion_b200.unet import UNet2DModel
     from oracle import torch_ref as O
 
+    monkeypatch.setenv("BD_NO_GN_SUMS", "1")   # bitwise comparison of two runs: the run-to-run reproducible forward plan
     cfg = dict(O.TINY_CONFIG, block_out_channels=(64, 128))
     sd0 = O.make_state_dict(cfg, 2)
     S, B = 32, 8

@@ -348,10 +348,11 @@ def test_pndm_pipeline_matches_reference(golden):
 
 def test_groupnorm_statistics_plan(monkeypatch):
     """GroupNorm fusion, step one, at the plan level: for the CIFAR10 UNet the engine routes 19 of the 51 forward GroupNorms
-    through producer-accumulated statistics (every norm2 at 32x32 / 16x16, every norm1 / attention norm whose input comes
-    from halo-kernel convs -- not conv_in's output, not 8x8 / 4x4), and eps_hat is the same function: equal to the plan
+    through producer-accumulated statistics by default (the halo-reuse 3x3 kernels at 32x32 / 16x16 deliver them) and ALL 51
+    with BD_GN_SUMS_GENERIC=1 (conv_in, the generic one-tile / split-K / persistent kernels, the stride-2 convs and the
+    attention projections too: built and correct, measured no faster, off by default); eps_hat is the same function: equal to the plan
     with the reducing kernels everywhere (BD_NO_GN_SUMS=1) up to the fp16 rounding noise the 19 re-rounded GroupNorm outputs
-    inject (measured MSE 2.7e-7, the size of the whole fp16-vs-fp32-oracle error; bound 5x)."""
+    inject (measured MSE 2.7e-7 with 19 of them, the size of the whole fp16-vs-fp32-oracle error; bound 5x)."""
     from oracle import torch_ref as O
 
     m, _ = _model(O.CIFAR10_CONFIG)
@@ -361,6 +362,12 @@ def test_groupnorm_statistics_plan(monkeypatch):
     eng = m.engine(B, False)
     assert eng.gn_sums_layers == 19, eng.gn_sums_layers
     a = eng.forward(x, t).clone()
+    monkeypatch.setenv("BD_GN_SUMS_GENERIC", "1")
+    m._engines = {}
+    eng3 = m.engine(B, False)
+    assert eng3.gn_sums_layers == 51, eng3.gn_sums_layers
+    c = eng3.forward(x, t).clone()
+    monkeypatch.delenv("BD_GN_SUMS_GENERIC")
     monkeypatch.setenv("BD_NO_GN_SUMS", "1")
     m._engines = {}
     eng2 = m.engine(B, False)
@@ -370,6 +377,7 @@ def test_groupnorm_statistics_plan(monkeypatch):
     err = float(((a - b) ** 2).mean())
     print(f"eps_hat MSE, producer statistics vs reducing GroupNorm kernels: {err:.3e}")
     assert err <= 1.5e-6
+    assert float(((c - b) ** 2).mean()) <= 3e-6
 
 
 def test_every_layer_of_the_cifar_unet_teacher_forced():
