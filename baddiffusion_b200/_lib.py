@@ -58,7 +58,7 @@ _SIGS = {
     "bd_sgemm": (i32, [vp, i64, i64, vp, i64, i64, vp, i64, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_gn_workspace_floats": (sz, [i32, i32]),
     "bd_groupnorm_fwd": (i32, [vp, i64, vp, i64, vp, vp, vp, vp, i32, i32, i32, i32, f32, i32, vp]),
-    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
+    "bd_groupnorm_bwd": (i32, [vp, i64, vp, i64, vp, i64, vp, i64, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp, i32, i32, i32, i32, i32, vp]),
     "bd_conv_fwd": (i32, [C.POINTER(ConvArgs), vp]),
     "bd_conv_fwd_gn_sums_supported": (i32, [C.POINTER(ConvArgs)]),
     "bd_groupnorm_apply_sums": (i32, [vp, i64, vp, i64, vp, vp, vp, i64, vp, i32, i32, i32, i32, f32, i32, vp]),

@@ -365,7 +365,8 @@ __global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restri
 template <bool GSUM>
 __global__ void __launch_bounds__(256, GSUM ? 2 : 3) gn_bwd_apply_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
-    const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
+    const __half* __restrict__ add, int64_t ldadd, const __half* __restrict__ add2, int64_t ldadd2,
+    __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
     const float* __restrict__ gab, int HW, int C, int G, int asplits, int apply_silu, float* __restrict__ gsum,
     int64_t ld_gsum) {
@@ -396,6 +397,12 @@ __global__ void __launch_bounds__(256, GSUM ? 2 : 3) gn_bwd_apply_kernel(
       unpack8(*reinterpret_cast<const half8*>(x + row * ldx + v * 8), fx);
       unpack8(*reinterpret_cast<const half8*>(dy + row * lddy + v * 8), fd);
       if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+      if (add2) {   // second fan-in operand (only with add)
+        float fb[8];
+        unpack8(*reinterpret_cast<const half8*>(add2 + row * ldadd2 + v * 8), fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float dz = fd[k];
@@ -613,10 +620,11 @@ __global__ void __launch_bounds__(512, 2) gn_fwd_fused_kernel(const __half* __re
 // (gsum): they are the bias gradients of the convolution that made x and, for norm2, the time_emb_proj gradient
 // (D/models/resnet.py:574-580), which otherwise cost one extra pass over dx each.
 // dynamic smem: red[threads][16] f32 | chs[2][C] f32 | chs2[C] f32 | tot[2][C] f32 | gab[G][2] f32
-template <int VMAX, int MINB>
+template <int VMAX, int MINB, bool ADD2 = false>   // ADD2: a second gradient fan-in operand (dx += add + add2), own instantiation
 __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
-    const __half* __restrict__ add, int64_t ldadd, __half* __restrict__ dx, int64_t lddx,
+    const __half* __restrict__ add, int64_t ldadd, const __half* __restrict__ add2, int64_t ldadd2,
+    __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dgb_parts, float* __restrict__ gsum,
     int64_t ld_gsum, int HW, int C, int G, int apply_silu) {
@@ -763,6 +771,12 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
       unpack8(hx[i], fx);
       unpack8(hd[i], fd);
       if (add) unpack8(*reinterpret_cast<const half8*>(add + row * ldadd + v * 8), fa);
+      if (ADD2) {
+        float fb[8];
+        unpack8(*reinterpret_cast<const half8*>(add2 + row * ldadd2 + v * 8), fb);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+      }
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         const float dz = fd[k];
@@ -776,7 +790,7 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
   }
   constexpr int TU2 = VMAX == 0 ? 3 : 2;
   for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU2) {
-    half8 tx[TU2], td[TU2], ta[TU2];
+    half8 tx[TU2], td[TU2], ta[TU2], tb[ADD2 ? TU2 : 1];
 #pragma unroll
     for (int u = 0; u < TU2; ++u)
       if (p + u * rows < p1) {
@@ -784,6 +798,7 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
         tx[u] = *reinterpret_cast<const half8*>(x + row * ldx + v * 8);
         td[u] = *reinterpret_cast<const half8*>(dy + row * lddy + v * 8);
         if (add) ta[u] = *reinterpret_cast<const half8*>(add + row * ldadd + v * 8);
+        if (ADD2) tb[u] = *reinterpret_cast<const half8*>(add2 + row * ldadd2 + v * 8);
       }
 #pragma unroll
     for (int u = 0; u < TU2; ++u)
@@ -793,6 +808,12 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
         unpack8(tx[u], fx);
         unpack8(td[u], fd);
         if (add) unpack8(ta[u], fa);
+        if (ADD2) {
+          float fb[8];
+          unpack8(tb[u], fb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        }
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float dz = fd[k];
@@ -961,13 +982,13 @@ int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, 
 }
 
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
-                     void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
+                     const void* add_dx2, int64_t ld_add2, void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
                      float* dbeta, float* work, float* gsum, int64_t ld_gsum, float* dgb_parts, int B, int HW, int C, int G,
                      int apply_silu, void* stream) {
   BD_CHECK_ARG(x && dy && dx && gamma && beta && stats && work && (dgb_parts || (dgamma && dbeta)), "bd_groupnorm_bwd: null pointer");
   BD_CHECK_ARG(C % 8 == 0 && C % G == 0 && ld_x % 8 == 0 && ld_dy % 8 == 0 && ld_dx % 8 == 0 && C <= 2048 &&
-                   (!add_dx || ld_add % 8 == 0),
-               "bd_groupnorm_bwd: bad shape (C=%d G=%d)", C, G);
+                   (!add_dx || ld_add % 8 == 0) && (!add_dx2 || (add_dx && ld_add2 % 8 == 0)),
+               "bd_groupnorm_bwd: bad shape (C=%d G=%d; add_dx2 needs add_dx)", C, G);
   if (B == 0) return BD_OK;
   {
     int fthreads, cs;
@@ -976,11 +997,12 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
       const size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
       const bool stream_bwd = gn_env_int("BD_GN_BWD_STREAM", 0) != 0;
       // register budget: 128 / thread (2 blocks of 256); 80 or 64 registers spill 400-570 B per thread
-      cudaError_t e = launch_cluster(stream_bwd ? gn_bwd_fused_kernel<0, 3> : vmax == 8 ? gn_bwd_fused_kernel<8, 2> : gn_bwd_fused_kernel<4, 2>,
-                                     dim3(cs, B), fthreads, smem,
+      auto kern = add_dx2 ? (stream_bwd ? gn_bwd_fused_kernel<0, 3, true> : vmax == 8 ? gn_bwd_fused_kernel<8, 2, true> : gn_bwd_fused_kernel<4, 2, true>)
+                          : (stream_bwd ? gn_bwd_fused_kernel<0, 3> : vmax == 8 ? gn_bwd_fused_kernel<8, 2> : gn_bwd_fused_kernel<4, 2>);
+      cudaError_t e = launch_cluster(kern, dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
-                                     (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
-                                     dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu);
+                                     (const __half*)add_dx, ld_add, (const __half*)add_dx2, ld_add2, (__half*)dx, ld_dx, gamma, beta,
+                                     stats, dgamma, dbeta, dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu);
       if (e != cudaSuccess) { set_error("bd_groupnorm_bwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
       count_launch(1);
       BD_CHECK_LAUNCH();
@@ -997,12 +1019,12 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
   if (gsum) cudaMemset2DAsync(gsum, (size_t)ld_gsum * sizeof(float), 0, (size_t)C * sizeof(float), B, (cudaStream_t)stream);
   if (gsum)
     gn_bwd_apply_kernel<true><<<dim3(asplits, B), threads, (size_t)rows * C * sizeof(float), (cudaStream_t)stream>>>(
-        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
-        stats, gab, HW, C, G, asplits, apply_silu, gsum, ld_gsum);
+        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (const __half*)add_dx2, ld_add2,
+        (__half*)dx, ld_dx, gamma, beta, stats, gab, HW, C, G, asplits, apply_silu, gsum, ld_gsum);
   else
     gn_bwd_apply_kernel<false><<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
-        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (__half*)dx, ld_dx, gamma, beta,
-        stats, gab, HW, C, G, asplits, apply_silu, nullptr, 0);
+        (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (const __half*)add_dx2, ld_add2,
+        (__half*)dx, ld_dx, gamma, beta, stats, gab, HW, C, G, asplits, apply_silu, nullptr, 0);
   count_launch(3);
   BD_CHECK_LAUNCH();
   return BD_OK;

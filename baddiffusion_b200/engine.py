@@ -151,15 +151,16 @@ class UNetEngine:
         else:
             ops.groupnorm_fwd(x_t, y_t, gamma, beta, stats, self.gn_work, self.G, self.eps, silu)
 
-    def _gn_bwd(self, x, dy, dx, gamma, beta, stats, dgamma, dbeta, silu, add_dx=None, gsum=None):
+    def _gn_bwd(self, x, dy, dx, gamma, beta, stats, dgamma, dbeta, silu, add_dx=None, gsum=None, add_dx2=None):
         """GroupNorm backward whose dgamma / dbeta leave as per-sample partials (B, 2C) and are summed over the batch by
         the batched column-sum launch at the end of backward (no atomics: 128 samples x 2C same-address updates per
         layer otherwise)."""
         if os.environ.get("BD_GN_ATOMIC_DGB"):
-            ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, self.gn_work, self.G, silu, add_dx=add_dx, gsum=gsum)
+            ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, self.gn_work, self.G, silu, add_dx=add_dx, gsum=gsum,
+                              add_dx2=add_dx2)
             return
         ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, self.gn_work, self.G, silu, add_dx=add_dx, gsum=gsum,
-                          parts=self._gn_parts[dgamma.data_ptr()])
+                          parts=self._gn_parts[dgamma.data_ptr()], add_dx2=add_dx2)
 
     def _reg_gn(self, dgamma, dbeta):
         """Plan-build time: the per-sample {dbeta | dgamma} buffer of one GroupNorm and its two batch-sum jobs."""
@@ -469,8 +470,9 @@ class UNetEngine:
                     ops.conv_dgrad(dout, ws, x.g, ksize=1, residual=x.g if x_filled else None, impl=impl)
                     self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=x.g, gsum=xgs)
                 elif x_filled:
-                    ops.add_f16(x.g, dout, x.g)
-                    self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=x.g, gsum=xgs)
+                    # three-way fan-in in the GroupNorm backward itself: what is already in x.g + the residual branch + norm1's
+                    self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=x.g, add_dx2=dout,
+                                 gsum=xgs)
                 else:
                     self._gn_bwd(x.t, d_a1, x.g, n1w, n1b, st1, g["norm1.weight"], g["norm1.bias"], True, add_dx=dout, gsum=xgs)
 
@@ -548,8 +550,7 @@ class UNetEngine:
                 self._fork(lambda: ops.conv_wgrad(a, d_qkv, g_wqkv, g_bqkv, ksize=1, accumulate=True, impl=impl))
                 ops.conv_dgrad(d_qkv, wqkv, d_a, ksize=1, impl=impl)
                 if x_filled:
-                    ops.add_f16(x.g, dout, x.g)
-                    self._gn_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, False, add_dx=x.g, gsum=xgs)
+                    self._gn_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, False, add_dx=x.g, add_dx2=dout, gsum=xgs)
                 else:
                     self._gn_bwd(x.t, d_a, x.g, gnw, gnb, st, g_gnw, g_gnb, False, add_dx=dout, gsum=xgs)
 

@@ -139,7 +139,8 @@ def groupnorm_apply_sums(x, y, gamma, beta, sums, stats, G, eps, silu):
                                           B, H * W, Cc, G, float(eps), int(silu), _s()))
 
 
-def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None, parts=None):
+def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, add_dx=None, gsum=None, parts=None,
+                  add_dx2=None):
     """gsum: optional (B, C) f32 view (row stride free) that receives the per-sample channel sums of dx.
     parts: optional contiguous (B, 2C) f32 that receives the per-sample {dbeta | dgamma} terms instead of the atomic
     accumulation into dgamma / dbeta (sum over the batch with bias_from_gsum)."""
@@ -149,13 +150,17 @@ def groupnorm_bwd(x, dy, dx, gamma, beta, stats, dgamma, dbeta, work, G, silu, a
     pa, lda = (None, 0)
     if add_dx is not None:
         pa, lda, *_ = _view(add_dx)
+    pa2, lda2 = (None, 0)
+    if add_dx2 is not None:
+        assert add_dx is not None
+        pa2, lda2, *_ = _view(add_dx2)
     pg, ldg = (None, 0)
     if gsum is not None:
         assert gsum.dtype == torch.float32 and gsum.shape == (B, Cc) and gsum.stride(1) == 1
         pg, ldg = gsum.data_ptr(), gsum.stride(0)
     if parts is not None:
         assert parts.dtype == torch.float32 and parts.shape == (B, 2 * Cc) and parts.is_contiguous()
-    check(L.lib().bd_groupnorm_bwd(px, ldx, pdy, lddy, pa, lda, pdx, lddx, _p(gamma), _p(beta), _p(stats), _p(dgamma),
+    check(L.lib().bd_groupnorm_bwd(px, ldx, pdy, lddy, pa, lda, pa2, lda2, pdx, lddx, _p(gamma), _p(beta), _p(stats), _p(dgamma),
                                    _p(dbeta), _p(work), pg, ldg, _p(parts), B, H * W, Cc, G, int(silu), _s()))
 
 

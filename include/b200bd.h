@@ -136,15 +136,17 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
 size_t bd_gn_workspace_floats(int B, int G);
 int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
                      float* stats, float* work, int B, int HW, int C, int G, float eps, int apply_silu, void* stream);
-/* backward: dx = GN'(dy (* SiLU')) [+ add_dx]; dgamma / dbeta f32 are ACCUMULATED into (zero them first).
- * work: bd_gn_workspace_floats(B, C) floats.                                                          */
 /* GroupNorm (+SiLU) forward as a pure streaming pass over statistics that the producing conv accumulated (`sums`, see
  * bd_conv_args.gn_sums; channel c of x at sums[b*ld_sums + 2c]): D/models/resnet.py:553-559,588-591 without the
  * reduction pass.  stats (B,G,2) = {mean, rstd} out (nullable), as bd_groupnorm_fwd writes them for the backward. */
 int bd_groupnorm_apply_sums(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
                             const float* sums, int64_t ld_sums, float* stats, int B, int HW, int C, int G, float eps,
                             int apply_silu, void* stream);
+/* backward: dx = GN'(dy (* SiLU')) [+ add_dx [+ add_dx2]] (gradient fan-in of up to two more branches: the residual
+ * path and an earlier consumer's contribution, resnet.py:597-601 / the skip connections); dgamma / dbeta f32 are
+ * ACCUMULATED into (zero them first).  work: bd_gn_workspace_floats(B, C) floats.                                 */
 int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy, const void* add_dx, int64_t ld_add,
+                     const void* add_dx2, int64_t ld_add2,
                      void* dx, int64_t ld_dx, const float* gamma, const float* beta, const float* stats, float* dgamma,
                      float* dbeta, float* dgb_work,
                      float* gsum /* nullable: (B, C) f32 with row stride ld_gsum, OVERWRITTEN with the per-sample

@@ -185,6 +185,12 @@ def test_groupnorm_fwd_bwd(ops, B, C, H, silu):
     ref_sum = (xr.grad + addr).sum(dim=(2, 3))
     assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05
     assert bool((gsum_wide[:, C:] == 7.0).all())
+    # second fan-in operand (residual branch + an earlier consumer's gradient): dx = GN' + add + add2 in one launch
+    add2_32 = torch.randn_like(ref)
+    add2, add2r = nhwc_half(add2_32)
+    dx3 = torch.empty_like(x)
+    ops.groupnorm_bwd(x, dy, dx3, gamma, beta, stats, torch.zeros_like(dg), torch.zeros_like(db), work, G, silu, add_dx=add, add_dx2=add2)
+    assert (to_nchw(dx3) - (xr.grad + addr + add2r)).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
     # per-sample {dbeta | dgamma} partials instead of atomics: identical dx, batch sums equal the gradients
     parts = torch.empty(B, 2 * C, device="cuda")
     dx2 = torch.empty_like(x)
@@ -220,6 +226,13 @@ def test_groupnorm_cluster_geometries(ops, B, C, H):
     assert (dx.float().permute(0, 3, 1, 2) - xr.grad).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
     ref_sum = xr.grad.sum(dim=(2, 3))
     assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05 * H / 32
+    # two fan-in operands, in place (dx aliases add_dx) as the engine calls it
+    a1 = torch.randn(B, H, H, C, device="cuda").half()
+    a2 = torch.randn(B, H, H, C, device="cuda").half()
+    want = xr.grad + a1.float().permute(0, 3, 1, 2) + a2.float().permute(0, 3, 1, 2)
+    buf = a1.clone()
+    ops.groupnorm_bwd(x, dy, buf, gamma, beta, stats, torch.zeros_like(dg), torch.zeros_like(db), work, G, True, add_dx=buf, add_dx2=a2)
+    assert (buf.float().permute(0, 3, 1, 2) - want).abs().max() < 4e-3 * max(1.0, float(want.abs().max()))
 
 
 # ------------------------------------------------------------------------------------------------
