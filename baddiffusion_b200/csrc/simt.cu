@@ -329,79 +329,102 @@ __global__ void __launch_bounds__(256) sgemm_kernel(const float* __restrict__ A,
 // ---------------------------------------------------------------------------------------------
 // timestep embedding + MLP (one block per sample), fp32
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) temb_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
+constexpr int TEMB_SPB = 2;   // samples per block
+constexpr int TEMB_THREADS = 1024;
+__global__ void __launch_bounds__(TEMB_THREADS) temb_mlp_kernel(const int64_t* __restrict__ t, const float* __restrict__ w1,
                                                        const float* __restrict__ b1, const float* __restrict__ w2,
                                                        const float* __restrict__ b2, float* __restrict__ sin_out,
                                                        float* __restrict__ h1, float* __restrict__ emb,
-                                                       __half* __restrict__ silu_emb, int dim, int temb, int flip,
+                                                       __half* __restrict__ silu_emb, int B, int dim, int temb, int flip,
                                                        const float* __restrict__ freqs) {
   extern __shared__ float sm[];
-  float* se = sm;         // [dim]
-  float* sa = sm + dim;   // [temb]
-  const int b = blockIdx.x, half_dim = dim / 2;
-  const float tv = (float)t[b];
-  for (int i = threadIdx.x; i < half_dim; i += blockDim.x) {
+  float* se = sm;                      // [SPB][dim]
+  float* sa = sm + TEMB_SPB * dim;     // [SPB][temb]
+  // L2 prefetch of W1 / W2 first, so it overlaps the sin/cos prologue (see the note at the layer loop)
+  {
+    const size_t n1 = (size_t)temb * dim * sizeof(float), n2 = (size_t)temb * temb * sizeof(float);
+    const size_t first = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 128, stride = (size_t)gridDim.x * blockDim.x * 128;
+    for (size_t off = first; off < n1; off += stride)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(w1) + off));
+    for (size_t off = first; off < n2; off += stride)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(w2) + off));
+  }
+  const int b0 = blockIdx.x * TEMB_SPB, half_dim = dim / 2;
+  for (int i = threadIdx.x; i < TEMB_SPB * half_dim; i += blockDim.x) {
     // embeddings.py:41-52: emb = t * exp(-ln(10000) * i / (half - shift)); the frequency table is evaluated on the
     // host with the reference's own torch expression so the sin/cos arguments are bit-identical
-    float arg = __fmul_rn(tv, freqs[i]);
+    const int s = i / half_dim, f = i - s * half_dim, b = b0 + s < B ? b0 + s : B - 1;
+    float arg = __fmul_rn((float)t[b], freqs[f]);
     float sv = sinf(arg), cv = cosf(arg);
-    int is = flip ? half_dim + i : i, ic = flip ? i : half_dim + i;
-    se[is] = sv;
-    se[ic] = cv;
+    int is = flip ? half_dim + f : f, ic = flip ? f : half_dim + f;
+    se[s * dim + is] = sv;
+    se[s * dim + ic] = cv;
   }
   __syncthreads();
   if (sin_out)
-    for (int i = threadIdx.x; i < dim; i += blockDim.x) sin_out[(int64_t)b * dim + i] = se[i];
+    for (int i = threadIdx.x; i < TEMB_SPB * dim; i += blockDim.x)
+      if (b0 + i / dim < B) sin_out[(int64_t)b0 * dim + i] = se[i];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  // A warp owns 4 output rows at a time: 4 independent dot products keep 4x the loads in flight (the kernel is a
-  // chain of L2 round trips, not arithmetic).  Per-row accumulation order is unchanged (lane-strided k, then the
-  // shuffle tree), so results are bit-identical to the one-row-at-a-time form.
+  // The kernel is a chain of dependent load round trips, not arithmetic (84 MFLOP): W1 / W2 are the fp32 master weights, which
+  // Adam streamed out of L2 at the end of the previous step, so the first touch of every line is an HBM miss and a warp
+  // that walks its rows group by group pays ~40 HBM latencies in a row (ncu: every stall sample sits on the first FFMA
+  // after a load; 65 kcycles for one block's 1.25 MB).  Therefore: (a) the grid first PREFETCHES both matrices into L2
+  // (each line requested once, by whichever block owns it -- one bulk of independent requests), (b) the block is
+  // 32 warps so a warp walks only temb / (32 R) row groups per layer (20 dependent round trips in all instead of 40 with 8 warps), R = 4 rows at a time,
+  // every lane fetching 16 bytes of each, (c) two samples share one pass over the weights, (d) block i starts its row
+  // walk at a different rotation so the blocks do not queue on the same L2 slice, (e) after the butterfly every lane
+  // holds every sum, so lane s*R+j finishes (bias, SiLU, store) output (s, j) instead of lane 0 doing all of them in a
+  // row.  Per-(sample, row) accumulation order is fixed.
   constexpr int R = 4;
-  for (int n0 = warp * R; n0 < temb; n0 += nw * R) {
-    float acc[R];
+  const int groups = (temb + R - 1) / R, rot = (int)((blockIdx.x * 37u) % (unsigned)groups);
+  auto layer = [&](const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ in, int K, auto&& store) {
+    for (int gi = warp; gi < groups; gi += nw) {
+      int g = gi + rot;
+      if (g >= groups) g -= groups;
+      const int n0 = g * R;
+      float acc[TEMB_SPB][R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = 0.f;
-    for (int k = lane; k < dim; k += 32) {
-      const float sv = se[k];
+      for (int s = 0; s < TEMB_SPB; ++s)
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (n0 + j < temb) acc[j] = fmaf(w1[(int64_t)(n0 + j) * dim + k], sv, acc[j]);
-    }
+        for (int j = 0; j < R; ++j) acc[s][j] = 0.f;
+      for (int k = lane * 4; k < K; k += 128) {
+        float4 wv[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
+        for (int j = 0; j < R; ++j)
+          wv[j] = (n0 + j < temb) ? *reinterpret_cast<const float4*>(w + (int64_t)(n0 + j) * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (n0 + j < temb) {
-          float h = acc[j] + b1[n0 + j];
-          if (h1) h1[(int64_t)b * temb + n0 + j] = h;
-          sa[n0 + j] = silu_f(h);
+        for (int s = 0; s < TEMB_SPB; ++s) {
+          const float4 sv = *reinterpret_cast<const float4*>(in + s * K + k);
+#pragma unroll
+          for (int j = 0; j < R; ++j)
+            acc[s][j] = fmaf(wv[j].w, sv.w, fmaf(wv[j].z, sv.z, fmaf(wv[j].y, sv.y, fmaf(wv[j].x, sv.x, acc[s][j]))));
         }
+      }
+#pragma unroll
+      for (int s = 0; s < TEMB_SPB; ++s)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[s][j] = warp_sum(acc[s][j]);
+      float mine = 0.f;
+#pragma unroll
+      for (int s = 0; s < TEMB_SPB; ++s)
+#pragma unroll
+        for (int j = 0; j < R; ++j)
+          if (lane == s * R + j) mine = acc[s][j];
+      if (lane < TEMB_SPB * R) {
+        const int s = lane / R, n = n0 + lane % R;
+        if (n < temb && b0 + s < B) store(s, n, mine + bias[n]);
+      }
     }
-  }
+  };
+  layer(w1, b1, se, dim, [&](int s, int n, float h) {
+    if (h1) h1[(int64_t)(b0 + s) * temb + n] = h;
+    sa[s * temb + n] = silu_f(h);
+  });
   __syncthreads();
-  for (int n0 = warp * R; n0 < temb; n0 += nw * R) {
-    float acc[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = 0.f;
-    for (int k = lane; k < temb; k += 32) {
-      const float sv = sa[k];
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (n0 + j < temb) acc[j] = fmaf(w2[(int64_t)(n0 + j) * temb + k], sv, acc[j]);
-    }
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = warp_sum(acc[j]);
-    if (lane == 0) {
-#pragma unroll
-      for (int j = 0; j < R; ++j)
-        if (n0 + j < temb) {
-          float e = acc[j] + b2[n0 + j];
-          emb[(int64_t)b * temb + n0 + j] = e;
-          if (silu_emb) silu_emb[(int64_t)b * temb + n0 + j] = __float2half_rn(silu_f(e));
-        }
-    }
-  }
+  layer(w2, b2, sa, temb, [&](int s, int n, float e) {
+    emb[(int64_t)(b0 + s) * temb + n] = e;
+    if (silu_emb) silu_emb[(int64_t)(b0 + s) * temb + n] = __float2half_rn(silu_f(e));
+  });
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -742,9 +765,11 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
 int bd_temb_mlp(const int64_t* t, const float* w1, const float* b1, const float* w2, const float* b2, float* sin_out,
                 float* h1, float* emb, void* silu_emb_f16, int B, int dim, int temb, int flip_sin_to_cos,
                 const float* freqs, void* stream) {
-  BD_CHECK_ARG(t && w1 && b1 && w2 && b2 && emb && freqs && B > 0 && dim > 0 && dim % 2 == 0 && temb > 0, "bd_temb_mlp: bad argument");
-  temb_mlp_kernel<<<B, 256, (dim + temb) * sizeof(float), (cudaStream_t)stream>>>(
-      t, w1, b1, w2, b2, sin_out, h1, emb, (__half*)silu_emb_f16, dim, temb, flip_sin_to_cos, freqs);
+  BD_CHECK_ARG(t && w1 && b1 && w2 && b2 && emb && freqs && B > 0 && dim > 0 && dim % 4 == 0 && temb > 0 && temb % 4 == 0 &&
+                   !((uintptr_t)w1 & 15) && !((uintptr_t)w2 & 15),
+               "bd_temb_mlp: bad argument (dim, temb multiples of 4; 16-byte aligned weights)");
+  temb_mlp_kernel<<<ceil_div(B, TEMB_SPB), TEMB_THREADS, (size_t)TEMB_SPB * (dim + temb) * sizeof(float), (cudaStream_t)stream>>>(
+      t, w1, b1, w2, b2, sin_out, h1, emb, (__half*)silu_emb_f16, B, dim, temb, flip_sin_to_cos, freqs);
   count_launch(1);
   BD_CHECK_LAUNCH();
   return BD_OK;
