@@ -57,24 +57,35 @@ __device__ __forceinline__ double warp_sum_d(double v) {
   return v;
 }
 
-// 16-byte vector of 8 halfs
+// 16-byte vector of 8 halfs.  The payload is a uint4 on purpose: __half2 has user-provided copy operations, so a struct of
+// four __half2 is copied member by member and every load / store of it becomes four 32-bit accesses (LDG.E x4) instead
+// of one LDG.E.128 -- 4x the load/store instructions and L1 wavefronts in every streaming kernel.
 struct __align__(16) half8 {
-  __half2 a, b, c, d;
+  uint4 u;
 };
 
+__device__ __forceinline__ float2 h2f2_bits(unsigned int w) {
+  __half2 h;
+  *reinterpret_cast<unsigned int*>(&h) = w;
+  return __half22float2(h);
+}
+__device__ __forceinline__ unsigned int f2h2_bits(float lo, float hi) {
+  const __half2 h = __floats2half2_rn(lo, hi);
+  return *reinterpret_cast<const unsigned int*>(&h);
+}
 __device__ __forceinline__ void unpack8(const half8& v, float* f) {
   float2 t;
-  t = __half22float2(v.a); f[0] = t.x; f[1] = t.y;
-  t = __half22float2(v.b); f[2] = t.x; f[3] = t.y;
-  t = __half22float2(v.c); f[4] = t.x; f[5] = t.y;
-  t = __half22float2(v.d); f[6] = t.x; f[7] = t.y;
+  t = h2f2_bits(v.u.x); f[0] = t.x; f[1] = t.y;
+  t = h2f2_bits(v.u.y); f[2] = t.x; f[3] = t.y;
+  t = h2f2_bits(v.u.z); f[4] = t.x; f[5] = t.y;
+  t = h2f2_bits(v.u.w); f[6] = t.x; f[7] = t.y;
 }
 __device__ __forceinline__ half8 pack8(const float* f) {
   half8 v;
-  v.a = __floats2half2_rn(f[0], f[1]);
-  v.b = __floats2half2_rn(f[2], f[3]);
-  v.c = __floats2half2_rn(f[4], f[5]);
-  v.d = __floats2half2_rn(f[6], f[7]);
+  v.u.x = f2h2_bits(f[0], f[1]);
+  v.u.y = f2h2_bits(f[2], f[3]);
+  v.u.z = f2h2_bits(f[4], f[5]);
+  v.u.w = f2h2_bits(f[6], f[7]);
   return v;
 }
 

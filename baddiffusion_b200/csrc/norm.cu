@@ -845,6 +845,264 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// GroupNorm backward, shared-memory resident.  Same cluster-per-sample decomposition and the same arithmetic as
+// gn_bwd_fused_kernel, but the CTA's slice of x and dy is brought into shared memory by bulk async copies
+// (cp.async.bulk, one elected warp, completion on an mbarrier) instead of through registers:
+//   * every byte the CTA will ever read from x / dy is in flight from the first instruction, independent of the register
+//     budget (the register kernel keeps 4 rows per thread and RE-READS the other 12 of 16 in its second phase);
+//   * nothing is held in registers across the cluster exchange, so 3 CTAs of 256 threads fit an SM and one CTA's
+//     arithmetic (MUFU-bound silu') and cluster round trip overlap the other CTAs' copies;
+//   * dz = dy * silu'(z) is written back over dy in shared memory (fp16, exactly what the register kernel keeps), so the
+//     second phase does not evaluate silu' again.
+// Wide tensors are split at GROUP boundaries into `gridDim.z` independent channel chunks of Cs channels (groups do not
+// interact), so a slice is at most ~64 KB: 256 -> 2 x 128, 384 -> 4 x 96 channels at 32 x 32.
+// dynamic smem: sx[npx][Cs] f16 | sd[npx][Cs] f16 | red f32 (tot[2Cs], gab[2Gs] alias its head) | chs[2][Cs] | chs2[Cs] | mbarrier
+__device__ __forceinline__ uint32_t gn_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gn_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(gn_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(gn_smem_u32(bar))
+               : "memory");
+}
+
+// Block-wide per-channel sums of NV x 8 per-thread partials.  When a warp holds several rows of the same channel vectors
+// (32 % C8 == 0) they are folded by shuffles first, so the scratch is [NV*8][warps][C8] instead of [NV*8][rows][C8].
+template <int NV>
+__device__ __forceinline__ void gn_block_channel_sums_w(float* red, float* chs, float (*vals)[8], int rows, int C8, int C,
+                                                        int r, int v, bool fold) {
+  if (fold) {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        for (int off = C8; off < 32; off <<= 1) vals[j][k] += __shfl_xor_sync(0xffffffffu, vals[j][k], off);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane < C8) {
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) red[((j * 8 + k) * nw + warp) * C8 + v] = vals[j][k];
+    }
+    rows = nw;
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+#pragma unroll
+      for (int k = 0; k < 8; ++k) red[((j * 8 + k) * rows + r) * C8 + v] = vals[j][k];
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < NV * C; idx += blockDim.x) {
+    const int j = idx / C, rem = idx - j * C, k = rem / C8, vv = rem - k * C8;
+    const float* src = red + (size_t)((j * 8 + k) * rows) * C8 + vv;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int rr = 0;
+    for (; rr + 4 <= rows; rr += 4) {
+      a0 += src[(rr + 0) * C8];
+      a1 += src[(rr + 1) * C8];
+      a2 += src[(rr + 2) * C8];
+      a3 += src[(rr + 3) * C8];
+    }
+    for (; rr < rows; ++rr) a0 += src[rr * C8];
+    chs[j * C + vv * 8 + k] = (a0 + a1) + (a2 + a3);
+  }
+  __syncthreads();
+}
+
+template <bool ADD2>
+__global__ void __launch_bounds__(256, 3) gn_bwd_smem_kernel(
+    const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
+    const __half* __restrict__ add, int64_t ldadd, const __half* __restrict__ add2, int64_t ldadd2,
+    __half* __restrict__ dx, int64_t lddx,
+    const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dgb_parts, float* __restrict__ gsum,
+    int64_t ld_gsum, int HW, int C, int G, int Cs, int npx_max, int red_floats, int fold, int apply_silu) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  cg::cluster_group cl = cg::this_cluster();
+  const int CS = (int)cl.num_blocks(), rank = (int)cl.block_rank();
+  extern __shared__ __align__(128) unsigned char gsm[];
+  __half* sx = reinterpret_cast<__half*>(gsm);
+  __half* sd = sx + (size_t)npx_max * Cs;
+  float* red = reinterpret_cast<float*>(sd + (size_t)npx_max * Cs);
+  float* chs = red + red_floats;
+  float* chs2 = chs + 2 * Cs;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(chs2 + Cs);
+  const int cpg = C / G, Gs = Cs / cpg;
+  float* tot = red;            // both dead before red is used again (gsum)
+  float* gab = red + 2 * Cs;
+  const int C8 = Cs / 8, rows = blockDim.x / C8;
+  const int tid = threadIdx.x, v = tid % C8, r = tid / C8;
+  const int b = blockIdx.y, c0 = blockIdx.z * Cs, g0 = c0 / cpg;
+  const int p0 = (int)((int64_t)HW * rank / CS), p1 = (int)((int64_t)HW * (rank + 1) / CS), npx = p1 - p0;
+  const int64_t rb = (int64_t)b * HW + p0;   // first row of this CTA's slice
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(gn_smem_u32(bar)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
+  if (tid < 32) {
+    const uint32_t row_bytes = (uint32_t)Cs * 2;
+    if (tid == 0)
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(gn_smem_u32(bar)), "r"(2u * npx * row_bytes) : "memory");
+    __syncwarp();
+    if (ldx == Cs && lddy == Cs) {   // the slice is one contiguous run
+      if (tid == 0) gn_bulk_g2s(sx, x + rb * ldx, (uint32_t)npx * row_bytes, bar);
+      if (tid == 1) gn_bulk_g2s(sd, dy + rb * lddy, (uint32_t)npx * row_bytes, bar);
+    } else {
+      for (int p = tid; p < npx; p += 32) {
+        gn_bulk_g2s(sx + (size_t)p * Cs, x + (rb + p) * ldx + c0, row_bytes, bar);
+        gn_bulk_g2s(sd + (size_t)p * Cs, dy + (rb + p) * lddy + c0, row_bytes, bar);
+      }
+    }
+  }
+  // the fan-in operands are read in phase 2: pull their lines towards L2 now
+  if (add && (v & 7) == 0)
+    for (int p = r; p < npx; p += rows) {
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(add + (rb + p) * ldadd + c0 + v * 8));
+      if (ADD2) asm volatile("prefetch.global.L2 [%0];" ::"l"(add2 + (rb + p) * ldadd2 + c0 + v * 8));
+    }
+  float k1[8], cz[8];   // k1 = rstd*gamma ; z/2 = x*(k1/2) + cz
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int ch = c0 + v * 8 + k, g = ch / cpg;
+    k1[k] = stats[((int64_t)b * G + g) * 2 + 1] * gamma[ch];
+    cz[k] = 0.5f * (beta[ch] - stats[((int64_t)b * G + g) * 2 + 0] * k1[k]);
+  }
+  {
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0; selp.u32 %0, 1, 0, p; }"
+                   : "=r"(done) : "r"(gn_smem_u32(bar)) : "memory");
+  }
+  {
+    float ss[2][8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) ss[0][k] = ss[1][k] = 0.f;
+#pragma unroll 2
+    for (int p = r; p < npx; p += rows) {
+      float fx[8], fd[8];
+      unpack8(*reinterpret_cast<const half8*>(sx + (size_t)p * Cs + v * 8), fx);
+      half8* dzp = reinterpret_cast<half8*>(sd + (size_t)p * Cs + v * 8);
+      unpack8(*dzp, fd);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float dz = fd[k];
+        if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+        fd[k] = dz;
+        ss[0][k] += dz;
+        ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
+      }
+      if (apply_silu) *dzp = pack8(fd);   // keep dz, not dy: phase 2 does not evaluate silu' again (own element: no hazard)
+    }
+    gn_block_channel_sums_w<2>(red, chs, ss, rows, C8, Cs, r, v, fold != 0);
+  }
+  cl.sync();
+  for (int ch = tid; ch < Cs; ch += blockDim.x) {
+    float ra[GN_MAX_CS], rx[GN_MAX_CS];   // remote loads first, adds after (one DSMEM round trip)
+#pragma unroll
+    for (int rk = 0; rk < GN_MAX_CS; ++rk)
+      if (rk < CS) {
+        const float* rc = cl.map_shared_rank(chs, rk);
+        ra[rk] = rc[ch];
+        rx[rk] = rc[Cs + ch];
+      }
+    float sa = 0.f, sxx = 0.f;
+#pragma unroll
+    for (int rk = 0; rk < GN_MAX_CS; ++rk)
+      if (rk < CS) { sa += ra[rk]; sxx += rx[rk]; }
+    const int g = (c0 + ch) / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    const float sq = rstd * (sxx - mean * sa);   // sum dz*xhat = rstd * (sum dz*x - mean * sum dz)
+    tot[ch] = sa;
+    tot[Cs + ch] = sq;
+    if (rank == 0) {
+      if (dgb_parts) {   // per-sample partials, summed over the batch by bd_bias_from_gsum (no atomics, fixed order)
+        dgb_parts[(int64_t)b * 2 * C + c0 + ch] = sa;
+        dgb_parts[(int64_t)b * 2 * C + C + c0 + ch] = sq;
+      } else {
+        atomicAdd(dbeta + c0 + ch, sa);
+        atomicAdd(dgamma + c0 + ch, sq);
+      }
+    }
+  }
+  cl.barrier_arrive();
+  __syncthreads();
+  for (int g = tid; g < Gs; g += blockDim.x) {
+    double ga = 0.0, gq = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      ga += (double)gamma[c0 + c] * (double)tot[c];
+      gq += (double)gamma[c0 + c] * (double)tot[Cs + c];
+    }
+    const double n = (double)HW * cpg;
+    gab[2 * g] = (float)(ga / n);
+    gab[2 * g + 1] = (float)(gq / n);
+  }
+  __syncthreads();
+  float c1[8], cc0[8], so[1][8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int chl = v * 8 + k, g = (c0 + chl) / cpg;
+    const float mean = stats[((int64_t)b * G + g) * 2 + 0], rstd = stats[((int64_t)b * G + g) * 2 + 1];
+    const float gA = gab[2 * (g - g0)], gB = gab[2 * (g - g0) + 1];
+    c1[k] = -rstd * rstd * gB;
+    cc0[k] = rstd * (mean * rstd * gB - gA);
+    so[0][k] = 0.f;
+  }
+  constexpr int TU = 2;
+  for (int p = r; p < npx; p += rows * TU) {
+    half8 ta[TU], tb[ADD2 ? TU : 1];
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+      if (p + u * rows < npx) {
+        const int64_t row = rb + p + u * rows;
+        if (add) ta[u] = *reinterpret_cast<const half8*>(add + row * ldadd + c0 + v * 8);
+        if (ADD2) tb[u] = *reinterpret_cast<const half8*>(add2 + row * ldadd2 + c0 + v * 8);
+      }
+#pragma unroll
+    for (int u = 0; u < TU; ++u)
+      if (p + u * rows < npx) {
+        const int pp = p + u * rows;
+        float fx[8], fd[8], fa[8];
+        unpack8(*reinterpret_cast<const half8*>(sx + (size_t)pp * Cs + v * 8), fx);
+        unpack8(*reinterpret_cast<const half8*>(sd + (size_t)pp * Cs + v * 8), fd);
+        if (add) unpack8(ta[u], fa);
+        if (ADD2) {
+          float fb[8];
+          unpack8(tb[u], fb);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) fa[k] += fb[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          float o = fmaf(k1[k], fd[k], fmaf(c1[k], fx[k], cc0[k]));
+          if (add) o += fa[k];
+          fx[k] = o;
+          so[0][k] += o;
+        }
+        *reinterpret_cast<half8*>(dx + (rb + pp) * lddx + c0 + v * 8) = pack8(fx);
+      }
+  }
+  cl.barrier_wait();  // every CTA has finished reading chs[]
+  if (gsum) {         // uniform across the cluster
+    __syncthreads();  // tot / gab (aliases of red) are dead in every thread
+    gn_block_channel_sums_w<1>(red, chs2, so, rows, C8, Cs, r, v, fold != 0);
+    cl.sync();
+    for (int ch = rank * blockDim.x + tid; ch < Cs; ch += CS * blockDim.x) {
+      float ra[GN_MAX_CS];
+#pragma unroll
+      for (int rk = 0; rk < GN_MAX_CS; ++rk)
+        if (rk < CS) ra[rk] = cl.map_shared_rank(chs2, rk)[ch];
+      float sa = 0.f;
+#pragma unroll
+      for (int rk = 0; rk < GN_MAX_CS; ++rk)
+        if (rk < CS) sa += ra[rk];
+      gsum[(int64_t)b * ld_gsum + c0 + ch] = sa;
+    }
+    cl.sync();
+  }
+}
+
 }  // namespace bd
 
 using namespace bd;
@@ -873,6 +1131,41 @@ static bool gn_fused_geometry(int B, int HW, int C, int max_threads, int vmax, i
   if (ceil_div(ceil_div(HW, c), rows) > 32) return false;
   *cs = c;
   return true;
+}
+
+
+// Geometry of gn_bwd_smem_kernel: channel chunks (a divisor of G, chunk a multiple of 8 channels), 256-ish threads =
+// C8 * rows, the smallest cluster whose slice (x + dy) plus scratch fits three CTAs per SM; grown while the grid is
+// under two waves.  False when no such geometry exists (large images: the streaming kernels serve those).
+struct GnBwdSmemGeo { int threads, cs, nchunk, Cs, npx_max, red_floats, fold; size_t smem; };
+static bool gn_bwd_smem_geometry(int B, int HW, int C, int G, GnBwdSmemGeo* o) {
+  if (gn_env_int("BD_GN_BWD_SMEM", 0) == 0 || getenv("BD_GN_V1")) return false;   // opt-in: measured slower
+  const size_t budget = (size_t)gn_env_int("BD_GN_BWD_SMEM_KB", 74) * 1024;
+  const int cpg = C / G;
+  for (int nch = 1; nch <= G; nch *= 2) {
+    if (G % nch) break;
+    const int Cs = C / nch;
+    if (Cs % 8 || Cs % cpg || Cs / 8 > 256) continue;
+    const int C8 = Cs / 8;
+    int rows = 256 / C8;
+    if (rows > HW) rows = HW;
+    const int threads = C8 * rows;
+    const int fold = (C8 < 32 && 32 % C8 == 0 && threads % 32 == 0) ? 1 : 0;
+    int red_floats = fold ? 16 * (threads / 32) * C8 : threads * 16;
+    if (red_floats < 2 * Cs + 2 * (Cs / cpg)) red_floats = 2 * Cs + 2 * (Cs / cpg);
+    auto bytes = [&](int c) {
+      return (size_t)2 * ceil_div(HW, c) * Cs * 2 + (size_t)red_floats * 4 + (size_t)3 * Cs * 4 + 16;
+    };
+    int c = 1;
+    while (c < GN_MAX_CS && (bytes(c) > budget || ceil_div(HW, c) < 1)) c *= 2;
+    if (bytes(c) > budget) continue;
+    while (c < GN_MAX_CS && (int64_t)B * c * nch < 2 * num_sms() && HW / (2 * c) >= rows) c *= 2;
+    if (HW / c < 1) continue;
+    o->threads = threads; o->cs = c; o->nchunk = nch; o->Cs = Cs; o->npx_max = ceil_div(HW, c);
+    o->red_floats = red_floats; o->fold = fold; o->smem = bytes(c);
+    return true;
+  }
+  return false;
 }
 
 template <typename... KArgs, typename... Args>
@@ -990,6 +1283,26 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
                    (!add_dx || ld_add % 8 == 0) && (!add_dx2 || (add_dx && ld_add2 % 8 == 0)),
                "bd_groupnorm_bwd: bad shape (C=%d G=%d; add_dx2 needs add_dx)", C, G);
   if (B == 0) return BD_OK;
+  {
+    GnBwdSmemGeo geo;
+    const bool aligned = !(((uintptr_t)x | (uintptr_t)dy | (uintptr_t)dx | (uintptr_t)add_dx | (uintptr_t)add_dx2) & 15);
+    if (aligned && HW >= gn_env_int("BD_GN_BWD_SMEM_MINHW", 64) && gn_bwd_smem_geometry(B, HW, C, G, &geo)) {
+      auto kern = add_dx2 ? gn_bwd_smem_kernel<true> : gn_bwd_smem_kernel<false>;
+      static bool attr_set[2] = {false, false};
+      if (!attr_set[add_dx2 ? 1 : 0]) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+        attr_set[add_dx2 ? 1 : 0] = true;
+      }
+      cudaError_t e = launch_cluster(kern, dim3(geo.cs, B, geo.nchunk), geo.threads, geo.smem, geo.cs, (cudaStream_t)stream,
+                                     (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add,
+                                     (const __half*)add_dx2, ld_add2, (__half*)dx, ld_dx, gamma, beta, stats, dgamma, dbeta,
+                                     dgb_parts, gsum, ld_gsum, HW, C, G, geo.Cs, geo.npx_max, geo.red_floats, geo.fold, apply_silu);
+      if (e != cudaSuccess) { set_error("bd_groupnorm_bwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
+      count_launch(1);
+      BD_CHECK_LAUNCH();
+      return BD_OK;
+    }
+  }
   {
     int fthreads, cs;
     const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;

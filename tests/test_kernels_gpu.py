@@ -235,6 +235,44 @@ def test_groupnorm_cluster_geometries(ops, B, C, H):
     assert (buf.float().permute(0, 3, 1, 2) - want).abs().max() < 4e-3 * max(1.0, float(want.abs().max()))
 
 
+@pytest.mark.parametrize("B,C,H,smem", [(6, 128, 32, 1), (6, 256, 32, 1), (3, 384, 32, 1), (4, 256, 16, 1), (4, 512, 16, 1),
+                                        (6, 256, 8, 1), (6, 128, 32, 0)])
+def test_groupnorm_bwd_strided_views(ops, monkeypatch, B, C, H, smem):
+    """x, dy, the fan-in operands and dx as channel slices of wider NHWC buffers (the zero-copy concat layout of the up
+    blocks), with the shared-memory-resident kernel (bulk async copies row by row, channel chunks at group boundaries)
+    and with the register kernel; both against torch and against each other within fp16 rounding."""
+    monkeypatch.setenv("BD_GN_BWD_SMEM", str(smem))
+    torch.manual_seed(2)
+    G, eps, pad = 32, 1e-6, 64
+    wide = lambda: torch.randn(B, H, H, C + pad, device="cuda").half()
+    xw, dyw, aw, a2w, dxw = wide(), wide(), wide(), wide(), wide()
+    x, dy, a1, a2, dx = xw[..., 8:8 + C], dyw[..., 16:16 + C], aw[..., :C], a2w[..., pad:], dxw[..., 24:24 + C]
+    guard = dxw.clone()
+    gamma = torch.randn(C, device="cuda") * 0.2 + 1
+    beta = torch.randn(C, device="cuda") * 0.2
+    stats = torch.empty(B, G, 2, device="cuda")
+    work = torch.empty(ops.gn_workspace_floats(B, C), device="cuda")
+    y = torch.empty(B, H, H, C, device="cuda", dtype=torch.half)
+    ops.groupnorm_fwd(x, y, gamma, beta, stats, work, G, eps, True)
+    xr = x.float().permute(0, 3, 1, 2).contiguous().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.silu(F.group_norm(xr, G, gr, br, eps)).backward(dy.float().permute(0, 3, 1, 2))
+    want = xr.grad + a1.float().permute(0, 3, 1, 2) + a2.float().permute(0, 3, 1, 2)
+    parts = torch.empty(B, 2 * C, device="cuda")
+    gsum = torch.empty(B, C, device="cuda")
+    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, None, None, work, G, True, add_dx=a1, add_dx2=a2, gsum=gsum, parts=parts)
+    assert (dx.float().permute(0, 3, 1, 2) - want).abs().max() < 4e-3 * max(1.0, float(want.abs().max()))
+    assert torch.equal(dxw[..., :24], guard[..., :24]) and torch.equal(dxw[..., 24 + C:], guard[..., 24 + C:])
+    assert rel_err(parts[:, C:].sum(0), gr.grad) < 2e-3 and rel_err(parts[:, :C].sum(0), br.grad) < 2e-3
+    ref_sum = want.sum(dim=(2, 3))
+    assert (gsum - ref_sum).abs().max() < 2e-3 * max(1.0, float(ref_sum.abs().max())) + 0.05
+    # atomics variant of the parameter gradients, no fan-in
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    ops.groupnorm_bwd(x, dy, dx, gamma, beta, stats, dg, db, work, G, True)
+    assert (dx.float().permute(0, 3, 1, 2) - xr.grad).abs().max() < 4e-3 * max(1.0, float(xr.grad.abs().max()))
+    assert rel_err(dg, gr.grad) < 2e-3 and rel_err(db, br.grad) < 2e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # convolution: fwd / dgrad / wgrad, CUDA-core and tcgen05 paths
 # ------------------------------------------------------------------------------------------------
