@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
     __half* __restrict__ dx, int64_t lddx,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
     float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dgb_parts, float* __restrict__ gsum,
-    int64_t ld_gsum, int HW, int C, int G, int apply_silu) {
+    int64_t ld_gsum, int HW, int C, int G, int apply_silu, int cache_dz) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");   // launched with programmatic stream serialization
   cg::cluster_group cl = cg::this_cluster();
@@ -638,6 +638,9 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
   float* chs2 = chs + 2 * C;
   float* tot = chs2 + C;
   float* gab = tot + 2 * C;
+  // cache_dz: dz = dy * silu'(z) of the rows that do not fit the register cache is parked here (fp16, [row][thread]) by
+  // phase 1, so phase 2 neither reads dy again nor evaluates silu' a second time for them
+  half8* dzc = reinterpret_cast<half8*>(gsm + (((size_t)blockDim.x * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4 + 15) & ~(size_t)15));
   const int C8 = C / 8, rows = blockDim.x / C8, cpg = C / G;
   const int tid = threadIdx.x, v = tid % C8, r = tid / C8;
   const int b = blockIdx.y;
@@ -654,11 +657,12 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
       hd[i] = *reinterpret_cast<const half8*>(db + (int64_t)p * lddy);
     }
   }
-  float k1[8], cz[8];   // k1 = rstd*gamma ; z/2 = x*(k1/2) + cz
+  float k1[8], hk[8], cz[8];   // k1 = rstd*gamma ; hk = k1/2 ; z/2 = x*hk + cz
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
     const int ch = v * 8 + k, g = ch / cpg;
     k1[k] = stats[((int64_t)b * G + g) * 2 + 1] * gamma[ch];
+    hk[k] = 0.5f * k1[k];
     cz[k] = 0.5f * (beta[ch] - stats[((int64_t)b * G + g) * 2 + 0] * k1[k]);   // h = z/2 = x*(k1/2) + cz
   }
   {
@@ -675,7 +679,7 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float dz = fd[k];
-          if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+          if (apply_silu) dz *= dsilu_h(fmaf(fx[k], hk[k], cz[k]));
           fd[k] = dz;
           ss[0][k] += dz;
           ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
@@ -684,7 +688,8 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
       }
     }
     constexpr int TU = VMAX == 0 ? 4 : 2;   // 2*TU loads in flight
-    for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU) {
+    int jt = 0;                             // index of the tail row (per thread)
+    for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU, jt += TU) {
       half8 tx[TU], td[TU];
 #pragma unroll
       for (int u = 0; u < TU; ++u)
@@ -701,10 +706,12 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             float dz = fd[k];
-            if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+            if (apply_silu) dz *= dsilu_h(fmaf(fx[k], hk[k], cz[k]));
+            fd[k] = dz;
             ss[0][k] += dz;
             ss[1][k] = fmaf(dz, fx[k], ss[1][k]);
           }
+          if (cache_dz) dzc[(size_t)(jt + u) * blockDim.x + tid] = pack8(fd);
         }
     }
     gn_block_channel_sums<2>(red, chs, ss, rows, C8, C, r, v);
@@ -789,14 +796,15 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
     }
   }
   constexpr int TU2 = VMAX == 0 ? 3 : 2;
-  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU2) {
+  int jt2 = 0;
+  for (int p = p0 + r + VMAX * rows; p < p1; p += rows * TU2, jt2 += TU2) {
     half8 tx[TU2], td[TU2], ta[TU2], tb[ADD2 ? TU2 : 1];
 #pragma unroll
     for (int u = 0; u < TU2; ++u)
       if (p + u * rows < p1) {
         const int64_t row = rb + p + u * rows;
         tx[u] = *reinterpret_cast<const half8*>(x + row * ldx + v * 8);
-        td[u] = *reinterpret_cast<const half8*>(dy + row * lddy + v * 8);
+        td[u] = cache_dz ? dzc[(size_t)(jt2 + u) * blockDim.x + tid] : *reinterpret_cast<const half8*>(dy + row * lddy + v * 8);
         if (add) ta[u] = *reinterpret_cast<const half8*>(add + row * ldadd + v * 8);
         if (ADD2) tb[u] = *reinterpret_cast<const half8*>(add2 + row * ldadd2 + v * 8);
       }
@@ -817,7 +825,7 @@ __global__ void __launch_bounds__(256, MINB) gn_bwd_fused_kernel(
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           float dz = fd[k];
-          if (apply_silu) dz *= dsilu_h(fmaf(fx[k], 0.5f * k1[k], cz[k]));
+          if (apply_silu && !cache_dz) dz *= dsilu_h(fmaf(fx[k], hk[k], cz[k]));
           float o = fmaf(k1[k], dz, fmaf(c1[k], fx[k], c0[k]));
           if (add) o += fa[k];
           fx[k] = o;
@@ -1147,7 +1155,8 @@ static bool gn_bwd_smem_geometry(int B, int HW, int C, int G, GnBwdSmemGeo* o) {
     const int Cs = C / nch;
     if (Cs % 8 || Cs % cpg || Cs / 8 > 256) continue;
     const int C8 = Cs / 8;
-    int rows = 256 / C8;
+    int rows = gn_env_int("BD_GN_BWD_SMEM_THREADS", 256) / C8;
+    if (rows < 1) continue;
     if (rows > HW) rows = HW;
     const int threads = C8 * rows;
     const int fold = (C8 < 32 && 32 % C8 == 0 && threads % 32 == 0) ? 1 : 0;
@@ -1307,15 +1316,21 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
     int fthreads, cs;
     const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;
     if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs)) {
-      const size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
+      size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
       const bool stream_bwd = gn_env_int("BD_GN_BWD_STREAM", 0) != 0;
+      // dz of the rows beyond the register cache parked in shared memory, while that leaves four CTAs per SM
+      const int C8f = C / 8, frows = fthreads / C8f;
+      const int tail_rows = ceil_div(ceil_div(HW, cs), frows) - (stream_bwd ? 0 : vmax);
+      const size_t dz_bytes = tail_rows > 0 ? (size_t)(tail_rows + 3) * fthreads * 16 : 0;
+      const int cache_dz = (tail_rows > 0 && gn_env_int("BD_GN_BWD_DZC", 1) && ((smem + 15) & ~(size_t)15) + dz_bytes <= 46 * 1024) ? 1 : 0;
+      if (cache_dz) smem = ((smem + 15) & ~(size_t)15) + dz_bytes;
       // register budget: 128 / thread (2 blocks of 256); 80 or 64 registers spill 400-570 B per thread
       auto kern = add_dx2 ? (stream_bwd ? gn_bwd_fused_kernel<0, 3, true> : vmax == 8 ? gn_bwd_fused_kernel<8, 2, true> : gn_bwd_fused_kernel<4, 2, true>)
                           : (stream_bwd ? gn_bwd_fused_kernel<0, 3> : vmax == 8 ? gn_bwd_fused_kernel<8, 2> : gn_bwd_fused_kernel<4, 2>);
       cudaError_t e = launch_cluster(kern, dim3(cs, B), fthreads, smem,
                                      cs, (cudaStream_t)stream, (const __half*)x, ld_x, (const __half*)dy, ld_dy,
                                      (const __half*)add_dx, ld_add, (const __half*)add_dx2, ld_add2, (__half*)dx, ld_dx, gamma, beta,
-                                     stats, dgamma, dbeta, dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu);
+                                     stats, dgamma, dbeta, dgb_parts, gsum, ld_gsum, HW, C, G, apply_silu, cache_dz);
       if (e != cudaSuccess) { set_error("bd_groupnorm_bwd: cluster launch failed: %s", cudaGetErrorString(e)); return BD_ERR_CUDA; }
       count_launch(1);
       BD_CHECK_LAUNCH();
