@@ -1315,7 +1315,10 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
   {
     int fthreads, cs;
     const int vmax = gn_env_int("BD_GN_VMAX", GN_VMAX) <= 4 ? 4 : 8;
-    if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs)) {
+    // 128 threads (4 CTAs / SM at 128 registers) is the faster shape wherever it can hold a sample; wide tensors at
+    // 32 x 32 (384 channels: 2 rows of 48 vectors) only fit the 32-rows-per-thread limit with 256
+    if (gn_fused_geometry(B, HW, C, gn_env_int("BD_GN_BT", 128), vmax, &fthreads, &cs) ||
+        (!getenv("BD_GN_BT") && gn_fused_geometry(B, HW, C, 256, vmax, &fthreads, &cs))) {
       size_t smem = (size_t)fthreads * 64 + (size_t)5 * C * 4 + (size_t)2 * G * 4;
       const bool stream_bwd = gn_env_int("BD_GN_BWD_STREAM", 0) != 0;
       // dz of the rows beyond the register cache parked in shared memory, while that leaves four CTAs per SM

@@ -75,3 +75,35 @@ for s, v in streams.items():
     print(f"stream {s}{' (main)' if s == main else ''}:")
     for k, (n, d) in sorted(agg.items(), key=lambda x: -x[1][1])[:14]:
         print(f"   {d:8.1f} us  n={n:3d}  avg={d / n:6.1f}  {k}")
+
+# Exposed time: walking each lane in launch order, the part of a kernel that runs after everything earlier on the lane
+# has ended (PDL-launched kernels start early and wait, so raw durations overlap).  Forward = everything before the
+# loss kernel; backward lanes = the stream that carries the GroupNorm backward (the dependent chain) and the others.
+def short(n):
+    return n.split("(")[0].replace("void ", "").replace("bd::", "").replace("umma::", "")[:52]
+
+
+def exposed(evs, t_begin):
+    agg, prev = {}, t_begin
+    for e in evs:
+        end = e["ts"] + e["dur"]
+        x = max(0.0, end - max(prev, e["ts"] if prev < e["ts"] else prev))
+        prev = max(prev, end)
+        n, d = agg.get(short(e["name"]), (0, 0.0))
+        agg[short(e["name"])] = (n + 1, d + x)
+    return agg
+
+
+loss_i = next(i for i, e in enumerate(step) if "mse_partial" in e["name"])
+t_loss = step[loss_i]["ts"]
+fwd = [e for e in step if e["ts"] < t_loss and e["args"].get("stream") == main]
+print(f"forward: {t_loss - t0:.1f} us")
+for k, (n, d) in sorted(exposed(fwd, t0).items(), key=lambda x: -x[1][1])[:12]:
+    print(f"   {d:8.1f} us exposed  n={n:3d}  avg={d / n:6.1f}  {k}")
+bwd = [e for e in step if e["ts"] >= t_loss]
+chain = next(e["args"].get("stream") for e in bwd if "gn_bwd" in e["name"])
+print(f"backward + optimizer: {end - (t_loss - t0):.1f} us; chain lane busy "
+      f"{sum(d for _, d in exposed([e for e in bwd if e['args'].get('stream') == chain], t_loss).values()):.0f} us, other lanes busy "
+      f"{sum(d for _, d in exposed([e for e in bwd if e['args'].get('stream') != chain], t_loss).values()):.0f} us")
+for k, (n, d) in sorted(exposed([e for e in bwd if e["args"].get("stream") == chain], t_loss).items(), key=lambda x: -x[1][1])[:16]:
+    print(f"   {d:8.1f} us exposed  n={n:3d}  avg={d / n:6.1f}  {k}")
