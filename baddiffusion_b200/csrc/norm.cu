@@ -49,10 +49,39 @@ static inline int gn_splits(int B, int HW, int rows, int per_sm) {
   return s < 1 ? 1 : s;
 }
 
+// one block per sample: (mean, rstd) per group from the split partials, fixed order, double accumulation
+// Runs in the CTA of gn_stats_kernel that finishes sample b last (partials come from other SMs: ld.global.cg).
+__device__ __forceinline__ void gn_finalize_body(const float* work, float* __restrict__ stats, int G, int splits, int HW,
+                                                 int cpg, float eps, int b) {
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double ds = 0.0, dq = 0.0;
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {   // 8 independent loads in flight per sum (same fixed order of the adds)
+      float2 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) w[u] = __ldcg(reinterpret_cast<const float2*>(work + (((int64_t)b * splits + sp + u) * G + g) * 2));
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { ds += (double)w[u].x; dq += (double)w[u].y; }
+    }
+    for (; sp < splits; ++sp) {
+      const float* w = work + (((int64_t)b * splits + sp) * G + g) * 2;
+      ds += (double)__ldcg(w);
+      dq += (double)__ldcg(w + 1);
+    }
+    const double n = (double)HW * cpg;
+    const double mean = ds / n;
+    double var = dq / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[((int64_t)b * G + g) * 2 + 0] = (float)mean;
+    stats[((int64_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
 // smem: red[rows][C][2]
 __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const __half* __restrict__ x, int64_t ldx, float* __restrict__ work, int HW, int C,
-                                int G, int splits) {
+                                int G, int splits, float* __restrict__ stats, int* __restrict__ counters, float eps) {
   extern __shared__ float red[];
+  __shared__ int s_last;
   const int C8 = C / 8, rows = blockDim.x / C8;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const int b = blockIdx.y, sp = blockIdx.x;
@@ -91,34 +120,14 @@ __global__ void __launch_bounds__(256, 4) gn_stats_kernel(const __half* __restri
     w[0] = (float)ds;
     w[1] = (float)dq;
   }
-}
-
-// one block per sample: (mean, rstd) per group from the split partials, fixed order, double accumulation
-__global__ void gn_finalize_kernel(const float* __restrict__ work, float* __restrict__ stats, int G, int splits, int HW,
-                                   int cpg, float eps) {
-  const int b = blockIdx.x;
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double ds = 0.0, dq = 0.0;
-    int sp = 0;
-    for (; sp + 8 <= splits; sp += 8) {   // 8 independent loads in flight per sum (same fixed order of the adds)
-      float2 w[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) w[u] = *reinterpret_cast<const float2*>(work + (((int64_t)b * splits + sp + u) * G + g) * 2);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) { ds += (double)w[u].x; dq += (double)w[u].y; }
-    }
-    for (; sp < splits; ++sp) {
-      const float* w = work + (((int64_t)b * splits + sp) * G + g) * 2;
-      ds += (double)w[0];
-      dq += (double)w[1];
-    }
-    const double n = (double)HW * cpg;
-    const double mean = ds / n;
-    double var = dq / n - mean * mean;
-    if (var < 0.0) var = 0.0;
-    stats[((int64_t)b * G + g) * 2 + 0] = (float)mean;
-    stats[((int64_t)b * G + g) * 2 + 1] = (float)(1.0 / sqrt(var + (double)eps));
-  }
+  // last CTA of the sample: (mean, rstd) per group (used to be a separate one-warp-per-sample launch)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == splits - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  gn_finalize_body(work, stats, G, splits, HW, cpg, eps, b);
 }
 
 // block = C8 * rows threads.  y = x * a + c  with a = rstd*gamma, c = beta - mean*a (per channel, in registers)
@@ -237,11 +246,64 @@ __global__ void __launch_bounds__(256, 4) gn_apply_sums_kernel(const __half* __r
 // backward pass 1: per (b, split, c): s1 = sum dz, s2 = sum dz * xhat    (dz = dy * silu'(z))
 // In the loop only  z = x*a + c  (a = rstd*gamma, c = beta - mean*a) is formed; sum dz*xhat is recovered from
 // sum dz*x afterwards, so the per-thread state is 4 x 8 registers.
+// per sample b: (1) channel sums over the split partials -> dgamma / dbeta contribution (fp32 atomics: one per
+// (sample, channel)), (2) per-group gA = sum_c gamma*s1 / n, gB = sum_c gamma*s2 / n -> gab (B, G, 2).
+// Runs in the last CTA of sample b of gn_bwd_reduce_kernel; the partials were written by other SMs, so they are read with
+// ld.global.cg (L2).  cs: shared scratch, [2][C] floats.
+__device__ __forceinline__ void gn_bwd_group_body(const float* work, const float* __restrict__ gamma,
+                                                  float* __restrict__ gab, float* __restrict__ dgamma,
+                                                  float* __restrict__ dbeta, float* __restrict__ dgb_parts, int HW, int C,
+                                                  int G, int splits, int b, float* cs) {
+  const int cpg = C / G;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    // 8 loads per sum in flight: with few samples (CelebA-HQ: B = 4 -> 4 CTAs) the split count is ~100 and a single
+    // dependent chain of L2 round trips made this tiny kernel 24 us; the summation order stays fixed
+    float a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float* w0 = work + ((int64_t)b * splits * 2) * C + c;
+    int sp = 0;
+    for (; sp + 8 <= splits; sp += 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a1[u] += __ldcg(w0 + (int64_t)(sp + u) * 2 * C);
+        a2[u] += __ldcg(w0 + (int64_t)(sp + u) * 2 * C + C);
+      }
+    }
+    for (; sp < splits; ++sp) {
+      a1[0] += __ldcg(w0 + (int64_t)sp * 2 * C);
+      a2[0] += __ldcg(w0 + (int64_t)sp * 2 * C + C);
+    }
+    const float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+    const float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+    cs[c] = s1;
+    cs[C + c] = s2;
+    if (dgb_parts) {
+      dgb_parts[(int64_t)b * 2 * C + c] = s1;
+      dgb_parts[(int64_t)b * 2 * C + C + c] = s2;
+    } else {
+      atomicAdd(dbeta + c, s1);
+      atomicAdd(dgamma + c, s2);
+    }
+  }
+  __syncthreads();
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    double a = 0.0, q = 0.0;
+    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+      a += (double)gamma[c] * (double)cs[c];
+      q += (double)gamma[c] * (double)cs[C + c];
+    }
+    const double n = (double)HW * cpg;
+    gab[((int64_t)b * G + g) * 2 + 0] = (float)(a / n);
+    gab[((int64_t)b * G + g) * 2 + 1] = (float)(q / n);
+  }
+}
+
 __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
     const __half* __restrict__ x, int64_t ldx, const __half* __restrict__ dy, int64_t lddy,
     const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ stats,
-    float* __restrict__ work, int HW, int C, int G, int splits, int apply_silu) {
+    float* __restrict__ work, int HW, int C, int G, int splits, int apply_silu, float* __restrict__ gab,
+    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ dgb_parts, int* __restrict__ counters) {
   extern __shared__ float red[];
+  __shared__ int s_last;
   const int C8 = C / 8, rows = blockDim.x / C8, cpg = C / G;
   const int v = threadIdx.x % C8, r = threadIdx.x / C8;
   const int b = blockIdx.y, sp = blockIdx.x;
@@ -307,57 +369,15 @@ __global__ void __launch_bounds__(256, 3) gn_bwd_reduce_kernel(
     w[ch] = sa;
     w[C + ch] = sq;
   }
-}
-
-// per sample b: (1) channel sums over the split partials -> dgamma / dbeta contribution (fp32 atomics: one per
-// (sample, channel)), (2) per-group gA = sum_c gamma*s1 / n, gB = sum_c gamma*s2 / n -> gab (B, G, 2).
-// smem: cs[2][C]
-__global__ void __launch_bounds__(256) gn_bwd_group_kernel(const float* __restrict__ work, const float* __restrict__ gamma,
-                                                           float* __restrict__ gab, float* __restrict__ dgamma,
-                                                           float* __restrict__ dbeta, float* __restrict__ dgb_parts, int HW,
-                                                           int C, int G, int splits) {
-  extern __shared__ float cs[];
-  const int b = blockIdx.x, cpg = C / G;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    // 8 loads per sum in flight: with few samples (CelebA-HQ: B = 4 -> 4 CTAs) the split count is ~100 and a single
-    // dependent chain of L2 round trips made this tiny kernel 24 us; the summation order stays fixed
-    float a1[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, a2[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float* w0 = work + ((int64_t)b * splits * 2) * C + c;
-    int sp = 0;
-    for (; sp + 8 <= splits; sp += 8) {
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        a1[u] += w0[(int64_t)(sp + u) * 2 * C];
-        a2[u] += w0[(int64_t)(sp + u) * 2 * C + C];
-      }
-    }
-    for (; sp < splits; ++sp) {
-      a1[0] += w0[(int64_t)sp * 2 * C];
-      a2[0] += w0[(int64_t)sp * 2 * C + C];
-    }
-    const float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
-    const float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
-    cs[c] = s1;
-    cs[C + c] = s2;
-    if (dgb_parts) {
-      dgb_parts[(int64_t)b * 2 * C + c] = s1;
-      dgb_parts[(int64_t)b * 2 * C + C + c] = s2;
-    } else {
-      atomicAdd(dbeta + c, s1);
-      atomicAdd(dgamma + c, s2);
-    }
-  }
+  // The CTA that finishes a sample last also folds the split partials into the per-group terms (what used to be a
+  // separate 4-CTA launch of ~20 us between the two passes at CelebA-HQ sizes).  counters[] is zeroed by the launcher.
+  __threadfence();
   __syncthreads();
-  for (int g = threadIdx.x; g < G; g += blockDim.x) {
-    double a = 0.0, q = 0.0;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-      a += (double)gamma[c] * (double)cs[c];
-      q += (double)gamma[c] * (double)cs[C + c];
-    }
-    const double n = (double)HW * cpg;
-    gab[((int64_t)b * G + g) * 2 + 0] = (float)(a / n);
-    gab[((int64_t)b * G + g) * 2 + 1] = (float)(q / n);
-  }
+  if (threadIdx.x == 0) s_last = atomicAdd(counters + b, 1) == splits - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  gn_bwd_group_body(work, gamma, gab, dgamma, dbeta, dgb_parts, HW, C, G, splits, b, red);
 }
 
 // backward pass 2:  dx = rstd*(dz*gamma - gA - xhat*gB) (+ add)  ==  k1*dz + c1*x + c0 (+ add)  with per-channel
@@ -1202,7 +1222,7 @@ extern "C" {
 
 size_t bd_gn_workspace_floats(int B, int C) {
   // forward needs B*splits*G*2 (G <= C), backward B*splits*2*C
-  return (size_t)(B > 0 ? B : 1) * ((size_t)gn_max_splits(B) * 2 * (size_t)C + 2 * (size_t)C);
+  return (size_t)(B > 0 ? B : 1) * ((size_t)gn_max_splits(B) * 2 * (size_t)C + 2 * (size_t)C + 1);   // + arrival counters
 }
 
 static inline void gn_geometry(int B, int HW, int C, int per_sm, int* threads, int* rows, int* splits, int* asplits) {
@@ -1241,14 +1261,15 @@ int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const f
   }
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 4, &threads, &rows, &splits, &asplits);
-  gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, work, HW, C, G, splits);
   // stats may be omitted by inference callers: park them behind the partials
   float* st = stats ? stats : work + (size_t)B * splits * 2 * C;
-  gn_finalize_kernel<<<B, 32, 0, (cudaStream_t)stream>>>(work, st, G, splits, HW, C / G, eps);
+  int* counters = reinterpret_cast<int*>(work + (size_t)B * ((size_t)gn_max_splits(B) * 2 * C + 2 * (size_t)C));
+  cudaMemsetAsync(counters, 0, (size_t)B * sizeof(int), (cudaStream_t)stream);
+  gn_stats_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x, ld_x, work, HW, C, G, splits, st, counters, eps);
   gn_apply_kernel<<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
       (const __half*)x, ld_x, (__half*)y, ld_y, gamma, beta, st, HW, C, G, asplits, apply_silu);
-  count_launch(3);
+  count_launch(2);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }
@@ -1342,11 +1363,13 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
   }
   int threads, rows, splits, asplits;
   gn_geometry(B, HW, C, 3, &threads, &rows, &splits, &asplits);
-  gn_bwd_reduce_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu);
-  // group sums live right behind the per-split partials in the workspace
+  // group sums live right behind the per-split partials in the workspace, the per-sample arrival counters at its end
   float* gab = work + (size_t)B * splits * 2 * C;
-  gn_bwd_group_kernel<<<B, 256, 2 * C * sizeof(float), (cudaStream_t)stream>>>(work, gamma, gab, dgamma, dbeta, dgb_parts, HW, C, G, splits);
+  int* counters = reinterpret_cast<int*>(work + (size_t)B * ((size_t)gn_max_splits(B) * 2 * C + 2 * (size_t)C));
+  cudaMemsetAsync(counters, 0, (size_t)B * sizeof(int), (cudaStream_t)stream);
+  gn_bwd_reduce_kernel<<<dim3(splits, B), threads, (size_t)rows * C * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)x, ld_x, (const __half*)dy, ld_dy, gamma, beta, stats, work, HW, C, G, splits, apply_silu, gab, dgamma, dbeta,
+      dgb_parts, counters);
   if (gsum) cudaMemset2DAsync(gsum, (size_t)ld_gsum * sizeof(float), 0, (size_t)C * sizeof(float), B, (cudaStream_t)stream);
   if (gsum)
     gn_bwd_apply_kernel<true><<<dim3(asplits, B), threads, (size_t)rows * C * sizeof(float), (cudaStream_t)stream>>>(
@@ -1356,7 +1379,7 @@ int bd_groupnorm_bwd(const void* x, int64_t ld_x, const void* dy, int64_t ld_dy,
     gn_bwd_apply_kernel<false><<<dim3(asplits, B), threads, 0, (cudaStream_t)stream>>>(
         (const __half*)x, ld_x, (const __half*)dy, ld_dy, (const __half*)add_dx, ld_add, (const __half*)add_dx2, ld_add2,
         (__half*)dx, ld_dx, gamma, beta, stats, gab, HW, C, G, asplits, apply_silu, nullptr, 0);
-  count_launch(3);
+  count_launch(2);
   BD_CHECK_LAUNCH();
   return BD_OK;
 }
