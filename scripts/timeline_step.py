@@ -96,7 +96,8 @@ def exposed(evs, t_begin):
 
 loss_i = next(i for i, e in enumerate(step) if "mse_partial" in e["name"])
 t_loss = step[loss_i]["ts"]
-fwd = [e for e in step if e["ts"] < t_loss and e["args"].get("stream") == main]
+fwd_lane = step[loss_i]["args"].get("stream")
+fwd = [e for e in step if e["ts"] < t_loss and e["args"].get("stream") == fwd_lane]
 print(f"forward: {t_loss - t0:.1f} us")
 for k, (n, d) in sorted(exposed(fwd, t0).items(), key=lambda x: -x[1][1])[:12]:
     print(f"   {d:8.1f} us exposed  n={n:3d}  avg={d / n:6.1f}  {k}")
