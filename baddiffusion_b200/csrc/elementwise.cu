@@ -181,10 +181,13 @@ __global__ void __launch_bounds__(256) ddpm_step_kernel(const float* __restrict_
   const float* c = coef + (size_t)row * 8;
   const float sb = c[0], sa = c[1], c0 = c[2], ct = c[3], sigma = c[4], clip = c[5], clipd = c[6];
   const bool has_noise = c[7] != 0.0f;
+  // c[7] = 1 + noise-stream id of this pipeline call (1.0 = stream 0): callers that draw a fresh id per call get fresh
+  // Philox noise from the same captured graph
+  const uint64_t stream_id = has_noise ? (uint64_t)(uint32_t)(c[7] - 1.0f) << 32 : 0;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 xv = reinterpret_cast<const float4*>(x)[i], ev = reinterpret_cast<const float4*>(eps)[i];
     float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + (uint64_t)row, i);
+    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + stream_id + (uint64_t)row, i);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -211,10 +214,11 @@ __global__ void __launch_bounds__(256) ddim_step_kernel(const float* __restrict_
   const float* c = coef + (size_t)row * 8;
   const float sb = c[0], sa = c[1], sap = c[2], dirc = c[3], stdv = c[4], clip = c[5];
   const bool reclip = c[6] != 0.0f, has_noise = stdv > 0.0f;
+  const uint64_t stream_id = (uint64_t)(uint32_t)c[7] << 32;   // c[7] = noise-stream id of this pipeline call (0 by default)
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 xv = reinterpret_cast<const float4*>(x)[i], ev = reinterpret_cast<const float4*>(eps)[i];
     float4 zv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + (uint64_t)row, i);
+    if (has_noise) zv = z ? reinterpret_cast<const float4*>(z)[i] : philox_normal4(seed, offset + stream_id + (uint64_t)row, i);
     float xs[4] = {xv.x, xv.y, xv.z, xv.w}, es[4] = {ev.x, ev.y, ev.z, ev.w}, zs[4] = {zv.x, zv.y, zv.z, zv.w}, o[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {

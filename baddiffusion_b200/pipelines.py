@@ -130,6 +130,16 @@ class _Pipeline:
         ts_dev = torch.as_tensor(np.asarray(timesteps, dtype=np.int64)).to(dev)
         coef = coef_table.to(dev).contiguous()
         cpu_gen = generator is not None and generator.device.type == "cpu"
+        if not cpu_gen and ddim != "pndm":
+            # Philox step noise: the captured graph bakes (seed, offset), so every call draws ONE id from the caller's
+            # generator (which advances it, like the reference's per-step randn calls would) and passes it through the
+            # spare column of the coefficient table -- fresh noise per call, reproducible after re-seeding, no re-capture
+            sid = float(int(torch.randint(0, 1 << 23, (1,), generator=generator, device=dev).item()))
+            coef = coef.clone()
+            if ddim:
+                coef[:, 7] = sid
+            else:
+                coef[:, 7] = torch.where(coef[:, 7] != 0, coef[:, 7] + sid, coef[:, 7])
         seed = (generator.initial_seed() if generator is not None else torch.initial_seed()) & ((1 << 63) - 1)
         key = (B, ddim, cpu_gen)
         st = self._graphs.get(key)

@@ -81,11 +81,14 @@ int bd_mse_fwd_bwd(const float* eps_hat, const float* target, float* loss, float
  * coef: DEVICE table of rows of 8 floats {sqrt_beta_prod_t, sqrt_alpha_prod_t, c0, ct, sigma, clip(<=0 off),
  * clip_defense(<=0 off), has_noise}; the host fills it with the reference's own 0-d fp32 torch expressions.
  * step_index: device int (nullable -> row 0) so one captured graph serves all 1000 steps.
- * z nullable -> Philox noise (seed, offset + *step_index).  In-place (x_prev == x) allowed.            */
+ * z nullable -> Philox noise (seed, offset + (id << 32) + *step_index), id = (uint32)(has_noise - 1): a caller that
+ * writes has_noise = 1 + id (id < 2^23, exact in fp32) into the table selects a fresh noise stream per pipeline call
+ * without re-capturing.  In-place (x_prev == x) allowed.                                               */
 int bd_ddpm_step(const float* x, const float* eps_hat, const float* z, float* x_prev, const float* coef,
                  const int* step_index, size_t n, uint64_t seed, uint64_t offset, void* stream);
 /* D/schedulers/scheduling_ddim.py:261-381.  coef row: {sqrt_beta_prod_t, sqrt_alpha_prod_t,
- * sqrt_alpha_prod_prev, dir_coef=(1-a_prev-std^2)^0.5, std, clip(<=0 off), use_clipped, 0}.          */
+ * sqrt_alpha_prod_prev, dir_coef=(1-a_prev-std^2)^0.5, std, clip(<=0 off), use_clipped, noise-stream id (0 default,
+ * < 2^23; Philox offset += id << 32)}.                                                                 */
 int bd_ddim_step(const float* x, const float* eps_hat, const float* z, float* x_prev, const float* coef,
                  const int* step_index, size_t n, uint64_t seed, uint64_t offset, void* stream);
 /* PNDM step (D/schedulers/scheduling_pndm.py:215-400 = step_prk / step_plms / _get_prev_sample, plus the clamp of the

@@ -255,6 +255,31 @@ def test_ddpm_1000_step_chain_matches_reference(golden):
     assert out.shape == ref.shape and d.mean() < 6e-4 and d.max() < 8e-3      # measured mean 1.1e-4, max 1.5e-3
 
 
+def test_device_generator_noise_is_fresh_per_call_and_reproducible(monkeypatch):
+    """Device-generator sampling (Philox step noise inside the captured graph): consecutive calls with the same generator
+    object must draw different step noise (the reference's generator advances with every randn), re-seeding must
+    reproduce the first call bitwise, and the graph is captured once."""
+    from baddiffusion_b200.pipelines import DDIMPipeline, DDPMPipeline
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from oracle import torch_ref as O
+
+    monkeypatch.setenv("BD_NO_GN_SUMS", "1")   # bitwise comparison of two runs: the reproducible plan
+    m, _ = _model(O.TINY_CONFIG)
+    init = torch.randn(3, 3, 32, 32, generator=torch.Generator().manual_seed(2))
+    for cls, kw in ((DDPMPipeline, {}), (DDIMPipeline, {"eta": 1.0})):
+        pipe = cls(unet=m, scheduler=DDPMScheduler(variance_type="fixed_large", clip_sample=True))
+        pipe.set_progress_bar_config(disable=True)
+        gen = torch.Generator(device="cuda").manual_seed(11)
+        a = pipe(batch_size=3, generator=gen, num_inference_steps=8, init=init, output_type=None, **kw).images
+        b = pipe(batch_size=3, generator=gen, num_inference_steps=8, init=init, output_type=None, **kw).images
+        graphs = [st["graph"] for st in pipe._graphs.values()]
+        gen.manual_seed(11)
+        c = pipe(batch_size=3, generator=gen, num_inference_steps=8, init=init, output_type=None, **kw).images
+        assert np.abs(a - b).mean() > 1e-3, "second call replayed the first call's noise"
+        assert np.array_equal(a, c)
+        assert [st["graph"] for st in pipe._graphs.values()] == graphs and len(graphs) == 1
+
+
 def test_teacher_forced_sampling_steps(golden):
     """Per-step parity without chaotic amplification: feed the ORACLE's x_t into one CUDA step (UNet + fused
     scheduler step) and compare x_{t-1}."""
