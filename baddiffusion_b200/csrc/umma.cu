@@ -62,6 +62,7 @@ struct FpropParams {
   int64_t ld_sums;
   int* error_flag;
   int dbg_shift, dbg_boff;  // bring-up experiment: A tile loaded dbg_shift rows early, descriptor start moved back
+  int epi_pre;              // bit 0: one-tile kernel, bit 1: persistent kernel fetch the residual before the accumulator wait
 };
 
 struct WgradParams {
@@ -219,14 +220,17 @@ __global__ void __launch_bounds__(320, BN == 256 ? 1 : 2) umma_fprop_kernel(cons
     const bool valid = n < p.NB && h < p.H && w < p.W;
     const int64_t mlin = ((int64_t)n * p.H + h) * p.W + w;                        // dense pixel index (rowbias)
     const int64_t m = (int64_t)n * p.out_sn + h * p.out_sh + w * p.out_sw + p.out_off;  // output / residual pixel
+    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32, p.gn_sums, p.ld_sums};
+    EpiResidual<BN / 2> pre;
+    const bool use_pre = (p.epi_pre & 1) && S == 1 && BN == 128 && p.residual != nullptr;   // in flight while the MMAs run
+    if (use_pre) epilogue_prefetch_residual<BN / 2>(pre, lane, m, valid, n_tile * BN + half * (BN / 2), e);
     const bool ok = mbar_wait(tmem_full, 0, p.error_flag, 3);
     tc_fence_after();
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * 32 * (BN / 2 + 4);  // operand stages are free now
-    EpiArgs e{p.bias, p.bias2, p.residual, p.ld_res, p.scale, p.y, p.ld_y, p.out_f32, p.gn_sums, p.ld_sums};
     if (S == 1) {
       if (ok)
         epilogue_warp<BN / 2, GNS>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane, m, mlin, valid,
-                                   n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+                                   n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW, use_pre ? &pre : nullptr);
     } else {
       if (ok) epilogue_stage_warp<BN / 2>(tmem_base + ((uint32_t)(q * 32) << 16) + half * (BN / 2), stage, lane);
       cluster_sync_all();   // every rank's partial tile is staged (all threads of the cluster take part, see below)
@@ -397,12 +401,15 @@ __global__ void __launch_bounds__(320, 1) umma_fprop_persistent_kernel(const __g
       const bool valid = n < p.NB && h < p.H && w < p.W;
       const int64_t mlin = ((int64_t)n * p.H + h) * p.W + w;
       const int64_t m = (int64_t)n * p.out_sn + h * p.out_sh + w * p.out_sw + p.out_off;
+      EpiResidual<BN / 2> pre;
+      const bool use_pre = (p.epi_pre & 2) && BN == 128 && p.residual != nullptr;   // in flight while this tile's MMAs run
+      if (use_pre) epilogue_prefetch_residual<BN / 2>(pre, lane, m, valid, n_tile * BN + half * (BN / 2), e);
       ok = mbar_wait(&tmem_full[buf], fph[buf], p.error_flag, 3);
       if (!ok) break;
       fph[buf] ^= 1;
       tc_fence_after();
       epilogue_warp<BN / 2, GNS>(tmem_base + ((uint32_t)(q * 32) << 16) + buf * BN + half * (BN / 2), stage, lane, m, mlin, valid,
-                                 n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW);
+                                 n_tile * BN + half * (BN / 2), e, p.rowbias, p.ld_rowbias, p.HW, use_pre ? &pre : nullptr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[buf]);
@@ -779,6 +786,7 @@ int fprop_launch(const FpropCall& c, cudaStream_t st) {
   p.y = c.y; p.ld_y = c.ld_y; p.out_f32 = c.out_f32;
   p.error_flag = error_flag();
   p.dbg_shift = (int)env_u32("BD_UMMA_DBG_SHIFT", 0);
+  p.epi_pre = (int)env_u32("BD_EPI_PRE", 3);
   p.dbg_boff = (int)env_u32("BD_UMMA_DBG_BOFF", 0);
 
   CUtensorMap ma0, ma1, mb, mb1;
