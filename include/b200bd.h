@@ -134,9 +134,12 @@ int bd_sgemm(const float* A, int64_t sam, int64_t sak, const float* Bm, int64_t 
 /* ------------------------------------------------------------------------------------------------
  * K4/K5  torch.nn.GroupNorm (+SiLU) on fp16 NHWC views; statistics in fp32 (two-stage, fixed order).
  * Call sites replaced: D/models/resnet.py:491,510,553-559,588-591; attention.py:64,126; unet_2d.py:312-313.
- *   x: (B,HW,C) view with ld_x; y likewise.  stats (B,G,2) f32 = {mean, rstd}.  work: (B,splits,G,2) f32.
+ *   x: (B,HW,C) view with ld_x; y likewise.  stats (B,G,2) f32 = {mean, rstd}.
+ *   work: bd_gn_workspace_floats(B, C) floats of scratch (per-split partials, group terms, and B arrival counters for
+ *   samples that are split over several CTAs: the CTA that finishes a sample last folds its partials).  One GroupNorm
+ *   call at a time per workspace; contents need no initialisation and are not preserved.
  * ---------------------------------------------------------------------------------------------- */
-size_t bd_gn_workspace_floats(int B, int G);
+size_t bd_gn_workspace_floats(int B, int C);
 int bd_groupnorm_fwd(const void* x, int64_t ld_x, void* y, int64_t ld_y, const float* gamma, const float* beta,
                      float* stats, float* work, int B, int HW, int C, int G, float eps, int apply_silu, void* stream);
 /* GroupNorm (+SiLU) forward as a pure streaming pass over statistics that the producing conv accumulated (`sums`, see
