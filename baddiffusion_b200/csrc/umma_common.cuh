@@ -272,17 +272,19 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
   // GNS: the RPI rows of one iteration belong to ONE sample (hosts enable it only for HW % 8 == 0 and tiles that hold whole
   // pixel groups of an image), so the sample index is warp-uniform and a change of it flushes the partials of the previous one
   float gs1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, gs2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int64_t cur_smp = -1;
+  int cur_smp = -1;
+  // sample index of this lane's own row, once (a 64-bit division per row and iteration otherwise)
+  const int smp_own = ((GNS || rowbias) && valid_own) ? (int)(mlin_own / HW) : -1;
 #pragma unroll
   for (int r0 = 0; r0 < 32; r0 += RPI) {
     const int row = r0 + rsub;
     const int64_t m = __shfl_sync(0xffffffffu, m_own, row);
-    const int64_t mlin = __shfl_sync(0xffffffffu, mlin_own, row);
     const int valid = __shfl_sync(0xffffffffu, (int)valid_own, row);
+    const int smp_row = __shfl_sync(0xffffffffu, smp_own, row);
     if (GNS) {
-      const int64_t smp = __shfl_sync(0xffffffffu, valid ? mlin / HW : (int64_t)-1, 0);   // lane 0's row speaks for the iteration
+      const int smp = __shfl_sync(0xffffffffu, smp_row, 0);   // lane 0's row speaks for the iteration
       if (smp != cur_smp) {
-        if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
+        if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + (int64_t)cur_smp * e.ld_sums + 2 * col, lane);
         cur_smp = smp;
       }
     }
@@ -291,7 +293,7 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
     const float4 a = *reinterpret_cast<const float4*>(sp), b = *reinterpret_cast<const float4*>(sp + 4);
     float f[8] = {a.x + bsum[0], a.y + bsum[1], a.z + bsum[2], a.w + bsum[3], b.x + bsum[4], b.y + bsum[5], b.z + bsum[6], b.w + bsum[7]};
     if (rowbias) {
-      const float* rb = rowbias + (mlin / HW) * ld_rowbias + col;
+      const float* rb = rowbias + (int64_t)smp_row * ld_rowbias + col;
       const float4 ra = *reinterpret_cast<const float4*>(rb), rc = *reinterpret_cast<const float4*>(rb + 4);
       f[0] += ra.x; f[1] += ra.y; f[2] += ra.z; f[3] += ra.w; f[4] += rc.x; f[5] += rc.y; f[6] += rc.z; f[7] += rc.w;
     }
@@ -323,7 +325,7 @@ __device__ __forceinline__ void epilogue_warp(uint32_t taddr, float* __restrict_
   }
   if (GNS) {
     __syncwarp();
-    if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + cur_smp * e.ld_sums + 2 * col, lane);
+    if (cur_smp >= 0) gn_sums_flush<LPR>(gs1, gs2, e.gn_sums + (int64_t)cur_smp * e.ld_sums + 2 * col, lane);
   }
   __syncwarp();
 }
