@@ -112,6 +112,47 @@ class Trainer:
         self.overlap_allreduce = (self.world > 1 and self.accum_steps == 1
                                   and os.environ.get("BD_NO_AR_OVERLAP", "0") != "1")
         self.launches_per_step = 0
+        # Host batches are copied on their own stream: the static input buffers are only read by the batch-prep kernel
+        # at the start of the forward/backward sequence, so the H2D copy of step i+1 may run while the optimizer of step
+        # i is still on the GPU; likewise `loss_item()` hands the loss to the host as soon as that sequence is done.
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._d2h_stream = torch.cuda.Stream(device=dev)
+        self._ev_seq_done = None                       # recorded after the sequence that reads the inputs / writes the loss
+        self._loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()
+
+    def _copy_in(self, pairs):
+        """(static device buffer, source) pairs.  Host sources go through the copy stream (ordered after the last reader of
+        the buffers, not after the optimizer); device sources may have been produced on the current stream: copied there."""
+        cur = torch.cuda.current_stream()
+        if any(src.is_cuda for _, src in pairs) or os.environ.get("BD_NO_COPY_STREAM"):
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
+            return
+        cs = self._copy_stream
+        if self._ev_seq_done is not None:
+            cs.wait_event(self._ev_seq_done)
+        else:
+            cs.wait_stream(cur)
+        with torch.cuda.stream(cs):
+            for dst, src in pairs:
+                dst.copy_(src, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(cs)
+        cur.wait_event(ev)
+
+    def loss_item(self) -> float:
+        """The loss of the last step as a Python float.  Waits for the forward/backward sequence only (a plain
+        `float(trainer.loss)` also waits for the optimizer, and the next batch's H2D copy behind it)."""
+        if self._ev_seq_done is None or os.environ.get("BD_NO_COPY_STREAM"):
+            return float(self.loss)
+        ds = self._d2h_stream
+        ds.wait_event(self._ev_seq_done)
+        with torch.cuda.stream(ds):
+            self._loss_host.copy_(self.loss, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(ds)
+        ev.synchronize()
+        return float(self._loss_host)
 
     # ------------------------------------------------------------------ the kernel sequence
     def _fwd_bwd(self, philox_noise: bool, part: Optional[int] = None, zero: bool = True):
@@ -186,14 +227,14 @@ class Trainer:
                    t: Optional[torch.Tensor] = None):
         """Host (pinned) or device tensors -> the static device buffers.  `t` / `noise` default to the reference's
         draws: t = randint on the device (baddiffusion.py:600); noise in-kernel (Philox) unless given."""
-        self.img.copy_(image, non_blocking=True)
-        self.isp.copy_(is_poison.to(torch.uint8), non_blocking=True)
+        pairs = [(self.img, image), (self.isp, is_poison.to(torch.uint8))]
+        if t is not None:
+            pairs.append((self.t, t))
+        if noise is not None:
+            pairs.append((self.noise, noise))
+        self._copy_in(pairs)
         if t is None:
             self.t.copy_(torch.randint(0, self.T, (self.B,), device=self.dev))
-        else:
-            self.t.copy_(t, non_blocking=True)
-        if noise is not None:
-            self.noise.copy_(noise, non_blocking=True)
 
     def step(self, image: torch.Tensor, is_poison: torch.Tensor, noise: Optional[torch.Tensor] = None,
              t: Optional[torch.Tensor] = None) -> torch.Tensor:
@@ -209,20 +250,23 @@ class Trainer:
         a quarter of the fp32 batch's H2D bytes, and no CPU-side ToTensor / normalize / flip (dataset.py:120-136)."""
         if not self.u8_input:
             raise RuntimeError("build the Trainer with u8_input=True to feed uint8 batches")
-        self.img_u8.copy_(image_u8, non_blocking=True)
-        self.flip.copy_(flip.to(torch.uint8), non_blocking=True)
-        self.isp.copy_(is_poison.to(torch.uint8), non_blocking=True)
+        pairs = [(self.img_u8, image_u8), (self.flip, flip.to(torch.uint8)), (self.isp, is_poison.to(torch.uint8))]
+        if t is not None:
+            pairs.append((self.t, t))
+        if noise is not None:
+            pairs.append((self.noise, noise))
+        self._copy_in(pairs)
         if t is None:
             self.t.copy_(torch.randint(0, self.T, (self.B,), device=self.dev))
-        else:
-            self.t.copy_(t, non_blocking=True)
-        if noise is not None:
-            self.noise.copy_(noise, non_blocking=True)
 
     def step_u8(self, image_u8: torch.Tensor, flip: torch.Tensor, is_poison: torch.Tensor,
                 noise: Optional[torch.Tensor] = None, t: Optional[torch.Tensor] = None) -> torch.Tensor:
         self.load_batch_u8(image_u8, flip, is_poison, noise, t)
         return self.step_resident(philox_noise=noise is None)
+
+    def _mark_seq_done(self):
+        self._ev_seq_done = torch.cuda.Event()
+        self._ev_seq_done.record()
 
     def step_resident(self, philox_noise: bool = True) -> torch.Tensor:
         """Same, with the batch already in the static device buffers (img / isp / t / noise)."""
@@ -241,6 +285,8 @@ class Trainer:
                     (self._g_fb if i == 0 else self._g_fb2[i - 1]).replay()
                 else:
                     self._fwd_bwd(philox_noise, i)
+                if i == 0:
+                    self._mark_seq_done()
                 for lo, hi in parts[i][2]:
                     works.append(dist.all_reduce(self.gflat[lo:hi], op=dist.ReduceOp.AVG, group=self.pg, async_op=True))
                     covered.append((lo, hi))
@@ -253,6 +299,7 @@ class Trainer:
                 (self._g_fb if first else self._g_fb_acc).replay()
             else:
                 self._fwd_bwd(philox_noise, zero=first)
+            self._mark_seq_done()
             if not last:
                 return self.loss
             if self.world > 1:

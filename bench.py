@@ -304,13 +304,15 @@ def measure_train(ctx, arch, K, W, e2e_steps=None):
     # end to end through the public API: pinned host batch -> H2D -> step -> loss D2H, every step
     K2 = e2e_steps or K
     for i in range(2):
-        tr.step(host[i % 4].image, host[i % 4].is_poison).item()
+        tr.step(host[i % 4].image, host[i % 4].is_poison)
+        tr.loss_item()
     ctx.barrier()
     e0.record()
     last = 0.0
     for i in range(K2):
         hb = host[i % 4]
-        last = tr.step(hb.image, hb.is_poison).item()
+        tr.step(hb.image, hb.is_poison)   # H2D of the pinned batch (copy stream) -> forward/backward -> optimizer
+        last = tr.loss_item()             # D2H of THIS step's loss, every step
     e1.record()
     ctx.barrier()
     ms_e2e = ctx.max_over_ranks(e0.elapsed_time(e1))
