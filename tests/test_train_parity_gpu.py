@@ -240,3 +240,51 @@ def test_trainer_u8_input_equals_fp32_input(monkeypatch):
         else:
             losses[mode] = float(tr.step(image, isp, noise=noise, t=t))
     assert losses["u8"] == losses["fp32"], losses
+
+
+def test_copy_stream_input_path_and_loss_item(monkeypatch):
+    """Host batches go through the Trainer's copy stream (ordered after the last reader of the static input buffers) and
+    `loss_item()` reads the loss right after forward/backward: four steps on different pinned host batches must give the
+    losses and parameters of the plain in-stream path (BD_NO_COPY_STREAM=1) -- bitwise for the first step, within the
+    run-to-run noise of the split-K weight-gradient reductions (fp32 `red.add` order) afterwards; a batch that arrived late
+    or was overwritten early would change the loss by O(1) -- and loss_item() == float(loss)."""
+    from baddiffusion_b200.dataset import Backdoor
+    from baddiffusion_b200.schedulers import DDPMScheduler
+    from baddiffusion_b200.train import Trainer
+    from baddiffusion_b200.unet import UNet2DModel
+    from oracle import torch_ref as O
+
+    monkeypatch.setenv("BD_NO_GN_SUMS", "1")   # bitwise comparison of two runs: the run-to-run reproducible forward plan
+    cfg = dict(O.TINY_CONFIG, block_out_channels=(64, 128))
+    sd0 = O.make_state_dict(cfg, 4)
+    S, B = 32, 8
+    bd = Backdoor(root="datasets")
+    trig = bd.get_trigger(type="BOX_14", channel=3, image_size=S)
+    targ = bd.get_target(type="HAT", trigger=trig)
+    batches, _ = _inputs(B, S, 4, seed=5)
+    batches = [tuple(x.pin_memory() for x in b) for b in batches]
+    isp = torch.tensor([i % 3 == 0 for i in range(B)]).to(torch.uint8).pin_memory()
+    out = {}
+    for mode in ("copy_stream", "in_stream"):
+        if mode == "in_stream":
+            monkeypatch.setenv("BD_NO_COPY_STREAM", "1")
+        m = UNet2DModel(**cfg)
+        m.load_state_dict(sd0)
+        m = m.cuda()
+        tr = Trainer(m, DDPMScheduler(variance_type="fixed_large"), B, trig, targ, lr=1e-3, total_steps=10, warmup_steps=0)
+        losses = []
+        for image, t, noise in batches:
+            dev_loss = tr.step(image, isp, noise=noise, t=t)
+            li = tr.loss_item()
+            assert li == float(dev_loss)
+            losses.append(li)
+        torch.cuda.synchronize()
+        out[mode] = (losses, tr.flat.clone())
+    la, lb = out["copy_stream"][0], out["in_stream"][0]
+    assert la[0] == lb[0], (la, lb)
+    assert all(abs(a - b) <= 2e-3 * abs(b) for a, b in zip(la, lb)), (la, lb)
+    pa, pb = out["copy_stream"][1], out["in_stream"][1]
+    rel = float((pa - pb).norm() / pb.norm())
+    print(f"copy stream vs in-stream after 4 steps: losses {la} / {lb}, parameter difference {rel:.2e} of the norm")
+    assert rel < 2.5e-4      # measured 2.5e-5 (run-to-run noise of the weight-gradient reductions); a wrong batch: > 1e-2
+    assert len(set(la)) == 4 and max(la) - min(la) > 0.1   # four different batches were really consumed
