@@ -286,5 +286,5 @@ def test_copy_stream_input_path_and_loss_item(monkeypatch):
     pa, pb = out["copy_stream"][1], out["in_stream"][1]
     rel = float((pa - pb).norm() / pb.norm())
     print(f"copy stream vs in-stream after 4 steps: losses {la} / {lb}, parameter difference {rel:.2e} of the norm")
-    assert rel < 2.5e-4      # measured 2.5e-5 (run-to-run noise of the weight-gradient reductions); a wrong batch: > 1e-2
+    assert rel < 1e-3        # measured 2.5e-5 (run-to-run noise of the weight-gradient reductions); a wrong batch: > 1e-2
     assert len(set(la)) == 4 and max(la) - min(la) > 0.1   # four different batches were really consumed
